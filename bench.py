@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- atoms/s for one CHGNet energy+forces(+stress) evaluation on perturbed diamond Si.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (libb200mlip, sm_100a)
+  python bench.py --impl reference --steps K --warmup W    # reference arm: CPU restatement of the
+                                                           # reference's path on the host cores
+
+Contract (see the task statement): one JSON line on stdout from rank 0.
+  value   = atoms / device time of forward+backward with the graph already resident in HBM
+            (CUDA events on the engine's compute stream, max over ranks)
+  e2e     = same metric through the public API (Potential_Dist.__call__) with HOST buffers:
+            pinned host positions -> GPU graph build -> forward -> backward -> forces back to host
+  roofline= edge-gather (atom conv forward) kernel, algorithmic bytes / event time / measured HBM peak
+Workload at N GPUs: n x n x (n*N) conventional Si cells, n = 23 (97 336 atoms per GPU; "100k"), slabs
+along z -> weak scaling.  Inputs (>300 MB of activations per pass) are far larger than the 126 MB L2.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "atoms/sec (energy+forces) CHGNet a-Si r_cut=5A"
+SURVEY_BYTES_PER_EDGE = 314.0  # SURVEY.md 8(d), rbf-recompute variant, D=64 fp32
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step(n_cells, threads):
+    """One bounded sample of the reference path on the host: the reference's own C graph builder
+    (oracle/_ref, P=2, rebuilt every call as pes.py:69-85 does) + the PyTorch restatement of the model
+    (forward + autograd backward).  Returns (atoms, seconds, detail)."""
+    import torch
+
+    from distmlip_b200.structures import si_diamond
+    from oracle import graph_ref as G
+    from oracle.chgnet_ref import CHGNetRef, build_line_graph
+
+    torch.set_num_threads(threads)
+    atoms = si_diamond(n_cells)
+    cart, lat, pbc = atoms.get_positions(), atoms.get_cell(), atoms.get_pbc().astype(np.int64)
+    t0 = time.perf_counter()
+    kind = "port"
+    t_graph = None
+    if G.load_ref_extension() is not None and n_cells >= 6:
+        frac = atoms.get_scaled_positions(wrap=True)
+        ref = G.ref_get_subgraphs(cart, frac, lat, pbc, 2, 5.0, 3.0, True, num_threads=threads)
+        t_graph = time.perf_counter() - t0
+        i1, i2, off = ref[5], ref[6], np.rint(ref[7]).astype(np.int64)
+        bond = np.zeros(len(i1), bool)
+        bond[ref[11]] = True
+    else:
+        i1, i2, off, _d2, bond = G.neighbor_list(cart, lat, pbc, 5.0, 3.0)
+        t_graph = time.perf_counter() - t0
+    bond_edges, la, lb, ce = build_line_graph(i1, i2, bond)  # not timed: python loop, the reference does this in C
+    model = cpu_reference_step.model = getattr(cpu_reference_step, "model", None) or CHGNetRef()
+    t = lambda a: torch.as_tensor(a, dtype=torch.int64)
+    lattice = torch.tensor(lat, dtype=torch.float32)
+    t1 = time.perf_counter()
+    strain = torch.zeros(3, 3, requires_grad=True)
+    L = lattice @ (torch.eye(3) + strain)
+    pos = torch.tensor(atoms.get_scaled_positions(False), dtype=torch.float32) @ L
+    pos.retain_grad()
+    vec = pos[t(i2)] + torch.tensor(off, dtype=torch.float32) @ L - pos[t(i1)]
+    types = torch.full((len(atoms),), model.element_types.index("Si"), dtype=torch.int64)
+    e, _ = model.forward_graph(pos, vec, t(i1), t(i2), t(bond_edges), t(la), t(lb), t(ce), types)
+    e.backward()
+    t_model = time.perf_counter() - t1
+    return len(atoms), t_graph + t_model, {"graph_s": t_graph, "model_s": t_model, "kind": kind}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    n_cells = 6  # 1728 atoms: a bounded sample of the same structure family
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_step(n_cells, cores)
+    ts, atoms = [], 0
+    for _ in range(args.steps):
+        atoms, sec, det = cpu_reference_step(n_cells, cores)
+        ts.append(sec)
+    sec = float(np.mean(ts))
+    val = atoms / sec
+    sample = (f"{atoms}-atom perturbed diamond Si (6x6x6 cells), reference C graph build (oracle/_ref, P=2, "
+              f"{det['graph_s']:.2f}s) + PyTorch-CPU restatement fwd+autograd bwd ({det['model_s']:.2f}s)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "atoms/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CHGNet energy+forces+stress, perturbed diamond Si, r_cut=5A r_bond=3A",
+                   "note": "bounded CPU sample of the same workload family"},
+        "cpu_baseline": {"value": val, "unit": "atoms/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from distmlip_b200.implementations.matgl import CHGNet_Dist, Potential_Dist
+    from distmlip_b200.structures import si_diamond
+    from tests._util import make_model  # random-init weights of the CHGNet architecture (seed 0)
+
+    n = args.cells
+    atoms = si_diamond(n, nz=n * world)
+    natoms = len(atoms)
+    model = CHGNet_Dist.from_existing(make_model())
+    model.enable_distributed_mode(list(range(world)) if world > 1 else [local])
+    pot = Potential_Dist(model=model, calc_forces=True, calc_stresses=True)
+    eng = model._engine
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-graph throughput (`value`) ----
+    out = pot(atoms)  # builds graph + first compute
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        eng.compute_resident(1)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, gather_ms, launches = 0.0, [], 0
+    for _ in range(args.steps):
+        _e, ms = eng.compute_resident(1)
+        dev_ms += ms
+        gather_ms.append(eng.timings()["edge_gather_ms"])
+        launches += eng.counts()["launches"]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = tmax.item() / args.steps
+    value = natoms / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API, host buffers in, forces out ----
+    # (Engine.set_structure stages positions/species through page-locked host buffers)
+    for _ in range(max(1, min(args.warmup, 2))):
+        pot(atoms)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = pot(atoms)
+        _ = float(out[0].item()) + float(out[1][0, 0])
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t2 = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = t2.item()
+    e2e_val = natoms / (e2e_ms * 1e-3)
+    tm = eng.timings()
+
+    if rank == 0:
+        c = eng.counts()
+        peak, peak_src = load_peaks()
+        g_ms = float(np.mean(gather_ms))
+        alg_bytes = SURVEY_BYTES_PER_EDGE * c["n_edges"]
+        n_loc, n_own = c["n_own"] + c["n_halo"], c["n_own"]
+        own_bytes = 28.0 * c["n_edges"] + 512.0 * n_loc + 512.0 * n_own + 256.0 * n_own + 0.75 * 512.0 * c["n_bond_own"]
+        achieved = alg_bytes / (g_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"CHGNet (random-init, seed 0) energy+forces+stress on {natoms}-atom perturbed "
+                                   f"diamond Si ({n}x{n}x{n * world} cells), r_cut=5A r_bond=3A, graph resident",
+                       "atoms": natoms, "atoms_per_gpu": natoms // world, "edges_per_gpu": c["n_edges"],
+                       "angles_per_gpu": c["n_angles"], "parallelism": f"slab{world}",
+                       "cache": "activations per pass >> 126 MB L2 (no explicit flush needed)"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "phase_ms": {"graph_build": tm["graph_ms"], "forward": tm["fwd_ms"], "backward": tm["bwd_ms"]},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "atoms/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": natoms * (24 + 4) + 72 + 12, "d2h_bytes_per_step": natoms * 12 + 8 + 36 + natoms * 4},
+            "roofline": {"bound": "hbm", "kernel": "k_atomconv_fwd (edge gather)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "bytes_per_launch": alg_bytes, "bytes_convention": "SURVEY 8(d): 314 B/edge",
+                         "kernel_ms": g_ms, "achieved_own_layout": own_bytes / (g_ms * 1e-3) / 1e9,
+                         "traffic": None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count()
+            a, sec, det = cpu_reference_step(6, cores)
+            line["cpu_baseline"] = {
+                "value": a / sec, "unit": "atoms/s", "cores": cores, "kind": "port",
+                "sample": f"{a}-atom Si (6x6x6), reference C graph build {det['graph_s']:.2f}s + PyTorch-CPU "
+                          f"restatement fwd+bwd {det['model_s']:.2f}s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=23, help="conventional cells per edge per GPU (23 -> 97 336 atoms)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

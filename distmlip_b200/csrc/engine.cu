@@ -1,0 +1,913 @@
+// engine.cu -- host orchestration behind the C-ABI (include/b200mlip.h):
+// weight composition, GPU-resident workspace, forward + hand-derived backward schedule, NCCL halo
+// exchange between slab neighbours, and the extern "C" entry points.
+//
+// Schedule mirrors (and is verified stage-by-stage against) oracle/manual_ref.py; the reference
+// control flow it replaces is DistMLIP/implementations/matgl/models/chgnet.py:208-453 (forward)
+// and pes.py:109-145 (scaling, autograd backward, forces, stress).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "graph.cuh"
+#include "kernels.cuh"
+
+namespace b2m {
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen: if torch already loaded its bundled libnccl.so.2 we reuse that copy.
+// ------------------------------------------------------------------------------------------
+struct Nccl {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  void load() {
+    if (lib) return;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    B2M_REQUIRE(lib != nullptr, B2M_ERR_CUDA, "cannot dlopen libnccl.so.2 (needed for world > 1)");
+#define L(name, sym)                                              \
+  *(void**)(&name) = dlsym(lib, sym);                             \
+  B2M_REQUIRE(name != nullptr, B2M_ERR_CUDA, "NCCL symbol missing: " sym)
+    L(GetUniqueId, "ncclGetUniqueId");
+    L(CommInitRank, "ncclCommInitRank");
+    L(CommDestroy, "ncclCommDestroy");
+    L(Send, "ncclSend");
+    L(Recv, "ncclRecv");
+    L(AllReduce, "ncclAllReduce");
+    L(GroupStart, "ncclGroupStart");
+    L(GroupEnd, "ncclGroupEnd");
+    L(GetErrorString, "ncclGetErrorString");
+#undef L
+  }
+};
+static Nccl g_nccl;
+#define NCCL_CK(call)                                                                              \
+  do {                                                                                             \
+    ncclResult_t r__ = (call);                                                                     \
+    if (r__ != ncclSuccess)                                                                        \
+      throw b2m::Error(B2M_ERR_CUDA, std::string("NCCL error: ") + g_nccl.GetErrorString(r__));   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+struct AtomLayerW {
+  float *W1s_k, *W1e_k, *W1t_k, *b1, *W1s_raw, *W1e_raw, *W1t_raw, *M, *W2k, *W2raw, *b2, *Wout_k, *Wout_raw;
+};
+struct BondLayerW {
+  float *W1a_k, *W1b_k, *W1c_k, *Wg_k, *b1, *W1a_raw, *W1b_raw, *W1c_raw, *Wg_raw, *W2k, *W2raw, *b2, *Wout_k, *Wout_raw;
+  float *WAa_k, *WAb_k, *WAc_k, *WAg_k, *bA, *WAa_raw, *WAb_raw, *WAc_raw, *WAg_raw;
+};
+
+}  // namespace b2m
+
+using namespace b2m;
+
+struct b2m_engine {
+  b2m_model_desc desc;
+  int device = 0;
+  cudaStream_t st = nullptr;
+  std::string err;
+  // weights
+  std::map<std::string, std::vector<float>> host_w;
+  std::map<std::string, std::vector<int64_t>> host_shape;
+  std::vector<double> elem_refs;
+  bool finalized = false;
+  DBuf<float> wbuf;
+  std::vector<AtomLayerW> aw;
+  std::vector<BondLayerW> bw;
+  float *d_emb = nullptr, *d_Wbe = nullptr, *d_Wae = nullptr, *d_Wabw = nullptr, *d_W3bw = nullptr, *d_fa = nullptr;
+  float *d_F0k = nullptr, *d_c0 = nullptr, *d_F0raw = nullptr, *d_F1k = nullptr, *d_c1 = nullptr, *d_F1raw = nullptr,
+        *d_F2 = nullptr, *d_Ws = nullptr, *d_eref = nullptr;
+  float c2 = 0.f, bs = 0.f;
+  RadialParams rp2, rp3;
+  // comm
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  // graph + workspace
+  Graph g;
+  bool have_graph = false;
+  std::vector<DBuf<float>> x, h, ang, upd;
+  DBuf<float> Ap, Cp, Qp, Ha, Hb, Xc, agg, aggB, y1p, y1, y2p, y2, e_atom, site;
+  DBuf<float> gx, gh, gang, gA, gC, gQ, gHa, gHb, gXc, gagg, gupd, gaggB, gd, gdb, gbvec, gy1, gy2;
+  DBuf<float> forces, sendbuf, recvbuf, site_full;
+  DBuf<double> scal;  // [0]=energy, [1..9]=virial
+  // timings
+  cudaEvent_t ev[8] = {nullptr};
+  double t_graph = 0, t_fwd = 0, t_bwd = 0, t_gather = 0, t_total = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gather_ev;
+  long long launches_last = 0;
+  double last_energy = 0;
+};
+
+namespace b2m {
+
+static const std::vector<float>& W(b2m_engine* e, const std::string& k, std::vector<int64_t> shape) {
+  auto it = e->host_w.find(k);
+  B2M_REQUIRE(it != e->host_w.end(), B2M_ERR_INVALID, "missing weight: " + k);
+  const auto& sh = e->host_shape[k];
+  size_t n = 1;
+  for (auto s : shape) n *= (size_t)s;
+  B2M_REQUIRE(it->second.size() == n && sh == shape, B2M_ERR_INVALID,
+              "weight '" + k + "' has an unsupported shape (engine supports dim=64, max_n=9, max_f=4)");
+  return it->second;
+}
+
+struct Packer {
+  std::vector<float> host;
+  size_t add(const std::vector<float>& v) {
+    size_t off = (host.size() + 63) / 64 * 64;  // 256 B alignment
+    host.resize(off + v.size());
+    memcpy(host.data() + off, v.data(), v.size() * sizeof(float));
+    return off;
+  }
+};
+
+// slice columns [c0, c0+64) of a row-major [rows][ncol] matrix -> [rows][64]
+static std::vector<float> cols(const std::vector<float>& m, int rows, int ncol, int c0) {
+  std::vector<float> o((size_t)rows * 64);
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < 64; c++) o[(size_t)r * 64 + c] = m[(size_t)r * ncol + c0 + c];
+  return o;
+}
+static std::vector<float> transpose(const std::vector<float>& m, int rows, int ncol) {
+  std::vector<float> o(m.size());
+  for (int r = 0; r < rows; r++)
+    for (int c = 0; c < ncol; c++) o[(size_t)c * rows + r] = m[(size_t)r * ncol + c];
+  return o;
+}
+static std::vector<float> vcat(const std::vector<float>& a, const std::vector<float>& b) {
+  std::vector<float> o(a);
+  o.insert(o.end(), b.begin(), b.end());
+  return o;
+}
+// [2][64][64] k-major from a stacked [128][64] raw block: out[br][k][n] = raw[br*64+n][k]
+static std::vector<float> branch_kmajor(const std::vector<float>& raw128x64) {
+  std::vector<float> o(2 * 64 * 64);
+  for (int br = 0; br < 2; br++)
+    for (int k = 0; k < 64; k++)
+      for (int n = 0; n < 64; n++) o[((size_t)br * 64 + k) * 64 + n] = raw128x64[((size_t)br * 64 + n) * 64 + k];
+  return o;
+}
+
+static void finalize_weights(b2m_engine* e) {
+  const int nb = e->desc.n_blocks;
+  for (auto& kv : e->host_w) {
+    const std::string& k = kv.first;
+    bool bad = k.find("atom_graph_layers") != std::string::npos &&
+               (k.find("edge_update_func") != std::string::npos || k.find("weight_func") != std::string::npos);
+    bad = bad || (k.find("bond_graph_layers") != std::string::npos && k.find("weight_func") != std::string::npos);
+    bad = bad || k.find("state_embedding") != std::string::npos || k.find("normalization") != std::string::npos;
+    B2M_REQUIRE(!bad, B2M_ERR_INVALID,
+                "unsupported CHGNet option (bond_update_hidden_dims / layer_bond_weights / state / norm): " + k);
+  }
+  Packer P;
+  std::map<std::string, size_t> off;
+  auto put = [&](const std::string& name, const std::vector<float>& v) { off[name] = P.add(v); };
+
+  const auto& f2 = W(e, "bond_expansion.frequencies", {NR});
+  const auto& f3 = W(e, "threebody_bond_expansion.frequencies", {NR});
+  const auto& fa = W(e, "angle_expansion.frequencies", {5});
+  for (int k = 0; k < NR; k++) {
+    e->rp2.freq[k] = f2[k];
+    e->rp3.freq[k] = f3[k];
+  }
+  e->rp2.rc = (float)e->desc.cutoff;
+  e->rp3.rc = (float)e->desc.three_body_cutoff;
+  e->rp2.norm = (float)std::sqrt(2.0 / e->desc.cutoff);
+  e->rp3.norm = (float)std::sqrt(2.0 / e->desc.three_body_cutoff);
+  e->rp2.p = e->rp3.p = e->desc.cutoff_exponent;
+  put("fa", fa);
+  put("emb", W(e, "atom_embedding.weight", {e->desc.n_elem, D}));
+  const auto& Wbe = W(e, "bond_embedding.layers.0.weight", {D, NR});
+  put("Wbe", Wbe);
+  put("Wae", W(e, "angle_embedding.layers.0.weight", {D, NF}));
+  put("Wabw", W(e, "atom_bond_weights.weight", {D, NR}));
+  put("W3bw", W(e, "threebody_bond_weights.weight", {D, NR}));
+
+  for (int l = 0; l < nb; l++) {
+    const std::string p = "atom_graph_layers." + std::to_string(l) + ".conv_layer.";
+    const auto W1 = vcat(W(e, p + "node_update_func.layers.layers.0.weight", {D, 3 * D}),
+                         W(e, p + "node_update_func.gates.layers.0.weight", {D, 3 * D}));  // [128][192]
+    const auto b1 = vcat(W(e, p + "node_update_func.layers.layers.0.bias", {D}),
+                         W(e, p + "node_update_func.gates.layers.0.bias", {D}));
+    const auto W1s = cols(W1, 128, 192, 0), W1e = cols(W1, 128, 192, 64), W1t = cols(W1, 128, 192, 128);
+    const auto W2 = vcat(W(e, p + "node_update_func.layers.layers.1.weight", {D, D}),
+                         W(e, p + "node_update_func.gates.layers.1.weight", {D, D}));
+    const auto b2 = vcat(W(e, p + "node_update_func.layers.layers.1.bias", {D}),
+                         W(e, p + "node_update_func.gates.layers.1.bias", {D}));
+    const auto& Wout = W(e, p + "node_out_func.weight", {D, D});
+    std::vector<float> M(128 * 9);
+    for (int j = 0; j < 128; j++)
+      for (int k = 0; k < 9; k++) {
+        double s = 0;
+        for (int c = 0; c < 64; c++) s += (double)W1e[(size_t)j * 64 + c] * (double)Wbe[(size_t)c * 9 + k];
+        M[j * 9 + k] = (float)s;
+      }
+    const std::string q = "a" + std::to_string(l) + ".";
+    put(q + "W1s_k", transpose(W1s, 128, 64));
+    put(q + "W1e_k", transpose(W1e, 128, 64));
+    put(q + "W1t_k", transpose(W1t, 128, 64));
+    put(q + "b1", b1);
+    put(q + "W1s_raw", W1s);
+    put(q + "W1e_raw", W1e);
+    put(q + "W1t_raw", W1t);
+    put(q + "M", M);
+    put(q + "W2k", branch_kmajor(W2));
+    put(q + "W2raw", W2);
+    put(q + "b2", b2);
+    put(q + "Wout_k", transpose(Wout, 64, 64));
+    put(q + "Wout_raw", Wout);
+  }
+  for (int l = 0; l < nb - 1; l++) {
+    const std::string p = "bond_graph_layers." + std::to_string(l) + ".conv_layer.";
+    const auto W1 = vcat(W(e, p + "node_update_func.layers.layers.0.weight", {D, 4 * D}),
+                         W(e, p + "node_update_func.gates.layers.0.weight", {D, 4 * D}));  // [128][256]
+    const auto b1 = vcat(W(e, p + "node_update_func.layers.layers.0.bias", {D}),
+                         W(e, p + "node_update_func.gates.layers.0.bias", {D}));
+    const auto W1a = cols(W1, 128, 256, 0), W1g = cols(W1, 128, 256, 64), W1c = cols(W1, 128, 256, 128),
+               W1b = cols(W1, 128, 256, 192);
+    const auto W2 = vcat(W(e, p + "node_update_func.layers.layers.1.weight", {D, D}),
+                         W(e, p + "node_update_func.gates.layers.1.weight", {D, D}));
+    const auto b2 = vcat(W(e, p + "node_update_func.layers.layers.1.bias", {D}),
+                         W(e, p + "node_update_func.gates.layers.1.bias", {D}));
+    const auto& Wout = W(e, p + "node_out_func.weight", {D, D});
+    const auto WA = vcat(W(e, p + "edge_update_func.layers.layers.0.weight", {D, 4 * D}),
+                         W(e, p + "edge_update_func.gates.layers.0.weight", {D, 4 * D}));
+    const auto bA = vcat(W(e, p + "edge_update_func.layers.layers.0.bias", {D}),
+                         W(e, p + "edge_update_func.gates.layers.0.bias", {D}));
+    const auto WAa = cols(WA, 128, 256, 0), WAg = cols(WA, 128, 256, 64), WAc = cols(WA, 128, 256, 128),
+               WAb = cols(WA, 128, 256, 192);
+    const std::string q = "b" + std::to_string(l) + ".";
+    put(q + "W1a_k", transpose(W1a, 128, 64));
+    put(q + "W1b_k", transpose(W1b, 128, 64));
+    put(q + "W1c_k", transpose(W1c, 128, 64));
+    put(q + "Wg_k", branch_kmajor(W1g));
+    put(q + "b1", b1);
+    put(q + "W1a_raw", W1a);
+    put(q + "W1b_raw", W1b);
+    put(q + "W1c_raw", W1c);
+    put(q + "Wg_raw", W1g);
+    put(q + "W2k", branch_kmajor(W2));
+    put(q + "W2raw", W2);
+    put(q + "b2", b2);
+    put(q + "Wout_k", transpose(Wout, 64, 64));
+    put(q + "Wout_raw", Wout);
+    put(q + "WAa_k", transpose(WAa, 128, 64));
+    put(q + "WAb_k", transpose(WAb, 128, 64));
+    put(q + "WAc_k", transpose(WAc, 128, 64));
+    put(q + "WAg_k", branch_kmajor(WAg));
+    put(q + "bA", bA);
+    put(q + "WAa_raw", WAa);
+    put(q + "WAb_raw", WAb);
+    put(q + "WAc_raw", WAc);
+    put(q + "WAg_raw", WAg);
+  }
+  const auto& F0 = W(e, "final_layer.layers.0.weight", {D, D});
+  const auto& F1 = W(e, "final_layer.layers.1.weight", {D, D});
+  put("F0k", transpose(F0, 64, 64));
+  put("F0raw", F0);
+  put("c0", W(e, "final_layer.layers.0.bias", {D}));
+  put("F1k", transpose(F1, 64, 64));
+  put("F1raw", F1);
+  put("c1", W(e, "final_layer.layers.1.bias", {D}));
+  put("F2", W(e, "final_layer.layers.2.weight", {1, D}));
+  e->c2 = W(e, "final_layer.layers.2.bias", {1})[0];
+  put("Ws", W(e, "sitewise_readout.weight", {1, D}));
+  e->bs = W(e, "sitewise_readout.bias", {1})[0];
+  if (!e->elem_refs.empty()) {
+    std::vector<float> r(e->elem_refs.begin(), e->elem_refs.end());
+    put("eref", r);
+  }
+  e->wbuf.ensure(P.host.size() + 64);
+  B2M_CK(cudaMemcpyAsync(e->wbuf.p, P.host.data(), P.host.size() * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  B2M_CK(cudaStreamSynchronize(e->st));
+  auto dp = [&](const std::string& n) { return e->wbuf.p + off.at(n); };
+  e->d_fa = dp("fa");
+  e->d_emb = dp("emb");
+  e->d_Wbe = dp("Wbe");
+  e->d_Wae = dp("Wae");
+  e->d_Wabw = dp("Wabw");
+  e->d_W3bw = dp("W3bw");
+  e->d_F0k = dp("F0k"), e->d_F0raw = dp("F0raw"), e->d_c0 = dp("c0");
+  e->d_F1k = dp("F1k"), e->d_F1raw = dp("F1raw"), e->d_c1 = dp("c1");
+  e->d_F2 = dp("F2"), e->d_Ws = dp("Ws");
+  e->d_eref = e->elem_refs.empty() ? nullptr : dp("eref");
+  e->aw.resize(nb);
+  for (int l = 0; l < nb; l++) {
+    const std::string q = "a" + std::to_string(l) + ".";
+    AtomLayerW& w = e->aw[l];
+    w.W1s_k = dp(q + "W1s_k"), w.W1e_k = dp(q + "W1e_k"), w.W1t_k = dp(q + "W1t_k"), w.b1 = dp(q + "b1");
+    w.W1s_raw = dp(q + "W1s_raw"), w.W1e_raw = dp(q + "W1e_raw"), w.W1t_raw = dp(q + "W1t_raw");
+    w.M = dp(q + "M"), w.W2k = dp(q + "W2k"), w.W2raw = dp(q + "W2raw"), w.b2 = dp(q + "b2");
+    w.Wout_k = dp(q + "Wout_k"), w.Wout_raw = dp(q + "Wout_raw");
+  }
+  e->bw.resize(nb - 1);
+  for (int l = 0; l < nb - 1; l++) {
+    const std::string q = "b" + std::to_string(l) + ".";
+    BondLayerW& w = e->bw[l];
+    w.W1a_k = dp(q + "W1a_k"), w.W1b_k = dp(q + "W1b_k"), w.W1c_k = dp(q + "W1c_k"), w.Wg_k = dp(q + "Wg_k");
+    w.b1 = dp(q + "b1"), w.W1a_raw = dp(q + "W1a_raw"), w.W1b_raw = dp(q + "W1b_raw"), w.W1c_raw = dp(q + "W1c_raw");
+    w.Wg_raw = dp(q + "Wg_raw"), w.W2k = dp(q + "W2k"), w.W2raw = dp(q + "W2raw"), w.b2 = dp(q + "b2");
+    w.Wout_k = dp(q + "Wout_k"), w.Wout_raw = dp(q + "Wout_raw");
+    w.WAa_k = dp(q + "WAa_k"), w.WAb_k = dp(q + "WAb_k"), w.WAc_k = dp(q + "WAc_k"), w.WAg_k = dp(q + "WAg_k");
+    w.bA = dp(q + "bA"), w.WAa_raw = dp(q + "WAa_raw"), w.WAb_raw = dp(q + "WAb_raw"), w.WAc_raw = dp(q + "WAc_raw");
+    w.WAg_raw = dp(q + "WAg_raw");
+  }
+  e->finalized = true;
+}
+
+// ------------------------------------------------------------------------------------------
+static void alloc_workspace(b2m_engine* e) {
+  Graph& g = e->g;
+  const int nb = e->desc.n_blocks;
+  const size_t nl = g.n_loc, no = g.n_own, bl = g.B_loc, bo = g.B_own;
+  const size_t A = (size_t)g.A, E = (size_t)g.E;
+  e->x.resize(nb + 1);
+  e->h.resize(nb);
+  e->ang.resize(nb - 1);
+  e->upd.resize(nb - 1);
+  for (auto& b : e->x) b.ensure(nl * D + 64);
+  for (auto& b : e->h) b.ensure(bl * D + 64);
+  for (auto& b : e->ang) b.ensure(A * D + 64);
+  for (auto& b : e->upd) b.ensure(bo * D + 64);
+  e->Ap.ensure(nl * D2 + 64), e->Cp.ensure(no * D2 + 64), e->Qp.ensure(bo * D2 + 64);
+  e->Ha.ensure(bl * D2 + 64), e->Hb.ensure(bo * D2 + 64), e->Xc.ensure(nl * D2 + 64);
+  e->agg.ensure(no * D + 64), e->aggB.ensure(bo * D + 64);
+  e->y1p.ensure(no * D), e->y1.ensure(no * D), e->y2p.ensure(no * D), e->y2.ensure(no * D);
+  e->e_atom.ensure(no), e->site.ensure(no);
+  e->gx.ensure(nl * D + 64), e->gh.ensure(bl * D + 64), e->gang.ensure(A * D + 64);
+  e->gA.ensure(nl * D2 + 64), e->gC.ensure(no * D2 + 64), e->gQ.ensure(bo * D2 + 64);
+  e->gHa.ensure(bl * D2 + 64), e->gHb.ensure(bo * D2 + 64), e->gXc.ensure(nl * D2 + 64);
+  e->gagg.ensure(no * D + 64), e->gupd.ensure(bo * D + 64), e->gaggB.ensure(bo * D + 64);
+  e->gd.ensure(E + 64), e->gdb.ensure(bl + 64), e->gbvec.ensure(bl * 3 + 64);
+  e->gy1.ensure(no * D), e->gy2.ensure(no * D);
+  e->forces.ensure((size_t)g.N * 3 + 64);
+  e->site_full.ensure((size_t)g.N + 64);
+  e->scal.ensure(16);
+  if (e->world > 1) {
+    size_t tot_to = 0, tot_bto = 0;
+    for (int q = 0; q < e->world; q++) tot_to += g.n_to[q], tot_bto += g.nb_to[q];
+    size_t m = std::max(tot_to * D, tot_bto * D);
+    e->sendbuf.ensure(m + 64);
+    e->recvbuf.ensure(m + 64);
+  }
+}
+
+// ---- halo exchange (NCCL p2p between slab neighbours) ----
+// forward: rows of `buf` listed in to_list[q] -> q's halo section; my halo section <- owners
+static void halo_forward(b2m_engine* e, float* buf, bool bonds) {
+  if (e->world <= 1) return;
+  Graph& g = e->g;
+  const int* nto = bonds ? g.nb_to : g.n_to;
+  const int* toff = bonds ? g.bto_off : g.to_off;
+  const int* nfrom = bonds ? g.nb_from : g.n_from;
+  const int* foff = bonds ? g.bfrom_off : g.from_off;
+  const int* list = bonds ? g.bto_list.p : g.to_list.p;
+  const size_t base = bonds ? (size_t)g.B_own : (size_t)g.n_own;
+  for (int q = 0; q < e->world; q++)
+    if (nto[q] > 0) launch_gather_rows(e->st, nto[q], D, list + toff[q], buf, e->sendbuf.p + (size_t)toff[q] * D);
+  NCCL_CK(g_nccl.GroupStart());
+  for (int q = 0; q < e->world; q++) {
+    if (q == e->rank) continue;
+    if (nto[q] > 0)
+      NCCL_CK(g_nccl.Send(e->sendbuf.p + (size_t)toff[q] * D, (size_t)nto[q] * D, ncclFloat32, q, e->comm, e->st));
+    if (nfrom[q] > 0)
+      NCCL_CK(g_nccl.Recv(buf + (base + foff[q]) * D, (size_t)nfrom[q] * D, ncclFloat32, q, e->comm, e->st));
+  }
+  NCCL_CK(g_nccl.GroupEnd());
+}
+// backward: my halo rows of the adjoint -> owners (accumulate), then zero the halo rows
+static void halo_backward(b2m_engine* e, float* gbuf, bool bonds) {
+  if (e->world <= 1) return;
+  Graph& g = e->g;
+  const int* nto = bonds ? g.nb_to : g.n_to;
+  const int* toff = bonds ? g.bto_off : g.to_off;
+  const int* nfrom = bonds ? g.nb_from : g.n_from;
+  const int* foff = bonds ? g.bfrom_off : g.from_off;
+  const int* list = bonds ? g.bto_list.p : g.to_list.p;
+  const size_t base = bonds ? (size_t)g.B_own : (size_t)g.n_own;
+  const size_t nhalo = bonds ? (size_t)g.B_halo : (size_t)g.n_halo;
+  NCCL_CK(g_nccl.GroupStart());
+  for (int q = 0; q < e->world; q++) {
+    if (q == e->rank) continue;
+    if (nfrom[q] > 0)
+      NCCL_CK(g_nccl.Send(gbuf + (base + foff[q]) * D, (size_t)nfrom[q] * D, ncclFloat32, q, e->comm, e->st));
+    if (nto[q] > 0)
+      NCCL_CK(g_nccl.Recv(e->recvbuf.p + (size_t)toff[q] * D, (size_t)nto[q] * D, ncclFloat32, q, e->comm, e->st));
+  }
+  NCCL_CK(g_nccl.GroupEnd());
+  for (int q = 0; q < e->world; q++)
+    if (nto[q] > 0)
+      launch_scatter_add_rows(e->st, nto[q], D, list + toff[q], e->recvbuf.p + (size_t)toff[q] * D, gbuf);
+  launch_zero_rows(e->st, gbuf + base * D, nhalo * D);
+}
+
+static AtomConvArgs atom_args(b2m_engine* e, int l) {
+  Graph& g = e->g;
+  const AtomLayerW& w = e->aw[l];
+  AtomConvArgs a;
+  memset(&a, 0, sizeof a);
+  a.E = g.E;
+  a.e_src = g.e_src.p, a.e_dst = g.e_dst.p, a.e_bond = g.e_bond.p, a.e_vec = g.e_vec.p;
+  a.Aproj = e->Ap.p, a.Cproj = e->Cp.p, a.Qproj = l > 0 ? e->Qp.p : nullptr;
+  a.M = w.M, a.W2k = w.W2k, a.W2raw = w.W2raw, a.b2 = w.b2, a.Wabw = e->d_Wabw;
+  a.rp = e->rp2;
+  return a;
+}
+static void atom_projections(b2m_engine* e, int l) {
+  Graph& g = e->g;
+  const AtomLayerW& w = e->aw[l];
+  launch_gemm(e->st, e->x[l].p, D, w.W1s_k, e->Ap.p, D2, g.n_loc, D2, D, nullptr, nullptr, 0, false);
+  launch_gemm(e->st, e->x[l].p, D, w.W1t_k, e->Cp.p, D2, g.n_own, D2, D, w.b1, nullptr, 0, false);
+  if (l > 0) launch_gemm(e->st, e->h[l].p, D, w.W1e_k, e->Qp.p, D2, g.B_own, D2, D, nullptr, nullptr, 0, false);
+}
+static void atom_layer_fwd(b2m_engine* e, int l) {
+  Graph& g = e->g;
+  const AtomLayerW& w = e->aw[l];
+  atom_projections(e, l);
+  launch_zero_rows(e->st, e->agg.p, (int64_t)g.n_own * D);
+  AtomConvArgs a = atom_args(e, l);
+  a.agg = e->agg.p;
+  cudaEvent_t e0, e1;
+  B2M_CK(cudaEventCreate(&e0));
+  B2M_CK(cudaEventCreate(&e1));
+  B2M_CK(cudaEventRecord(e0, e->st));
+  launch_atomconv_fwd(e->st, a);
+  B2M_CK(cudaEventRecord(e1, e->st));
+  e->gather_ev.push_back({e0, e1});
+  launch_gemm(e->st, e->agg.p, D, w.Wout_k, e->x[l + 1].p, D, g.n_own, D, D, nullptr, e->x[l].p, D, false);
+}
+// in: gx = dE/dx[l+1] (owned rows valid, halo rows zero).  out: gx = dE/dx[l] (all local rows)
+static void atom_layer_bwd(b2m_engine* e, int l) {
+  Graph& g = e->g;
+  const AtomLayerW& w = e->aw[l];
+  launch_gemm(e->st, e->gx.p, D, w.Wout_raw, e->gagg.p, D, g.n_own, D, D, nullptr, nullptr, 0, false);
+  atom_projections(e, l);
+  AtomConvArgs a = atom_args(e, l);
+  a.gagg = e->gagg.p;
+  a.gd = e->gd.p;
+  const bool need_gx = l > 0;
+  if (need_gx) {
+    launch_zero_rows(e->st, e->gA.p, (int64_t)g.n_loc * D2);
+    launch_zero_rows(e->st, e->gC.p, (int64_t)g.n_own * D2);
+    a.gA = e->gA.p, a.gC = e->gC.p, a.gQ = e->gQ.p;
+  }
+  launch_atomconv_bwd(e->st, a);
+  if (need_gx) {
+    launch_gemm(e->st, e->gA.p, D2, w.W1s_raw, e->gx.p, D, g.n_loc, D, D2, nullptr, nullptr, 0, true);
+    launch_gemm(e->st, e->gC.p, D2, w.W1t_raw, e->gx.p, D, g.n_own, D, D2, nullptr, nullptr, 0, true);
+    launch_gemm(e->st, e->gQ.p, D2, w.W1e_raw, e->gh.p, D, g.B_own, D, D2, nullptr, nullptr, 0, true);
+  }
+}
+
+static LineArgs line_args(b2m_engine* e, int l, bool hidden) {
+  Graph& g = e->g;
+  const BondLayerW& w = e->bw[l];
+  LineArgs a;
+  memset(&a, 0, sizeof a);
+  a.A = g.A;
+  a.a_in = g.a_in.p, a.a_out = g.a_out.p, a.a_ctr = g.a_ctr.p;
+  a.ang = e->ang[l].p;
+  a.Ha = e->Ha.p, a.Hb = e->Hb.p, a.Xc = e->Xc.p;
+  if (hidden) {
+    a.Wgk = w.Wg_k, a.Wgraw = w.Wg_raw, a.W2k = w.W2k, a.W2raw = w.W2raw, a.b2 = w.b2;
+  } else {
+    a.Wgk = w.WAg_k, a.Wgraw = w.WAg_raw;
+  }
+  return a;
+}
+static void line_projections(b2m_engine* e, int l, bool hidden) {
+  Graph& g = e->g;
+  const BondLayerW& w = e->bw[l];
+  const float* hsrc = hidden ? e->h[l].p : e->h[l + 1].p;
+  launch_gemm(e->st, hsrc, D, hidden ? w.W1a_k : w.WAa_k, e->Ha.p, D2, g.B_loc, D2, D, nullptr, nullptr, 0, false);
+  launch_gemm(e->st, hsrc, D, hidden ? w.W1b_k : w.WAb_k, e->Hb.p, D2, g.B_own, D2, D, hidden ? w.b1 : w.bA, nullptr,
+              0, false);
+  launch_gemm(e->st, e->x[l + 1].p, D, hidden ? w.W1c_k : w.WAc_k, e->Xc.p, D2, g.n_loc, D2, D, nullptr, nullptr, 0,
+              false);
+}
+static void line_bwd_common(b2m_engine* e, int l, bool hidden, LineArgs& a) {
+  Graph& g = e->g;
+  const BondLayerW& w = e->bw[l];
+  launch_zero_rows(e->st, e->gHa.p, (int64_t)g.B_loc * D2);
+  launch_zero_rows(e->st, e->gHb.p, (int64_t)g.B_own * D2);
+  launch_zero_rows(e->st, e->gXc.p, (int64_t)g.n_loc * D2);
+  a.gang = e->gang.p, a.gHa = e->gHa.p, a.gHb = e->gHb.p, a.gXc = e->gXc.p;
+  launch_line_bwd(e->st, a, hidden);
+  launch_gemm(e->st, e->gHa.p, D2, hidden ? w.W1a_raw : w.WAa_raw, e->gh.p, D, g.B_loc, D, D2, nullptr, nullptr, 0, true);
+  launch_gemm(e->st, e->gHb.p, D2, hidden ? w.W1b_raw : w.WAb_raw, e->gh.p, D, g.B_own, D, D2, nullptr, nullptr, 0, true);
+  launch_gemm(e->st, e->gXc.p, D2, hidden ? w.W1c_raw : w.WAc_raw, e->gx.p, D, g.n_loc, D, D2, nullptr, nullptr, 0, true);
+}
+
+static void forward(b2m_engine* e) {
+  Graph& g = e->g;
+  const int nb = e->desc.n_blocks;
+  launch_embed(e->st, g.n_loc, g.type.p, e->d_emb, e->x[0].p);
+  launch_bond_init(e->st, g.B_loc, g.b_vec.p, e->rp2, e->d_Wbe, e->h[0].p);
+  launch_angle_init(e->st, g.A, g.a_in.p, g.a_out.p, g.b_vec.p, e->d_fa, e->d_Wae, e->ang[0].p);
+  for (int l = 0; l < nb - 1; l++) {
+    atom_layer_fwd(e, l);
+    halo_forward(e, e->x[l + 1].p, false);
+    const BondLayerW& w = e->bw[l];
+    line_projections(e, l, true);
+    launch_zero_rows(e->st, e->aggB.p, (int64_t)g.B_own * D);
+    LineArgs a = line_args(e, l, true);
+    a.aggB = e->aggB.p;
+    launch_line_fwd(e->st, a, true);
+    launch_gemm(e->st, e->aggB.p, D, w.Wout_k, e->upd[l].p, D, g.B_own, D, D, nullptr, nullptr, 0, false);
+    launch_bond_update_fwd(e->st, g.B_own, g.b_vec.p, e->rp3, e->d_W3bw, e->h[l].p, e->upd[l].p, e->h[l + 1].p);
+    if (l < nb - 2) {
+      // the last block's angle update (and the halo copy of h feeding it) is dead code in the
+      // reference (chgnet.py:353-368 on the last iteration): nothing reads it afterwards.
+      halo_forward(e, e->h[l + 1].p, true);
+      line_projections(e, l, false);
+      LineArgs b = line_args(e, l, false);
+      b.ang_out = e->ang[l + 1].p;
+      launch_line_fwd(e->st, b, false);
+    }
+  }
+  // site-wise readout after block n-2 (chgnet.py:392-398)
+  launch_rowdot(e->st, g.n_own, e->x[nb - 1].p, e->d_Ws, e->bs, e->site.p, nullptr, nullptr, nullptr, 1.f);
+  atom_layer_fwd(e, nb - 1);
+  // final MLP 64 -> 64 -> 64 -> 1, sum (chgnet.py:422-440); E = std * E + mean (+ element refs) (pes.py:109-113)
+  launch_gemm(e->st, e->x[nb].p, D, e->d_F0k, e->y1p.p, D, g.n_own, D, D, e->d_c0, nullptr, 0, false);
+  launch_silu(e->st, (int64_t)g.n_own * D, e->y1p.p, e->y1.p);
+  launch_gemm(e->st, e->y1.p, D, e->d_F1k, e->y2p.p, D, g.n_own, D, D, e->d_c1, nullptr, 0, false);
+  launch_silu(e->st, (int64_t)g.n_own * D, e->y2p.p, e->y2.p);
+  B2M_CK(cudaMemsetAsync(e->scal.p, 0, 16 * sizeof(double), e->st));
+  launch_rowdot(e->st, g.n_own, e->y2.p, e->d_F2, e->c2, e->e_atom.p, e->scal.p, g.type.p, e->d_eref,
+                (float)e->desc.data_std);
+}
+
+static void backward(b2m_engine* e) {
+  Graph& g = e->g;
+  const int nb = e->desc.n_blocks;
+  launch_zero_rows(e->st, e->gd.p, g.E);
+  launch_zero_rows(e->st, e->gdb.p, g.B_loc);
+  launch_zero_rows(e->st, e->gbvec.p, (int64_t)g.B_loc * 3);
+  launch_zero_rows(e->st, e->gh.p, (int64_t)g.B_loc * D);
+  launch_zero_rows(e->st, e->gang.p, g.A * D);
+  launch_zero_rows(e->st, e->gx.p, (int64_t)g.n_loc * D);
+  launch_zero_rows(e->st, e->forces.p, g.N * 3);
+  // readout backward
+  launch_readout_seed(e->st, g.n_own, e->y2p.p, e->d_F2, (float)e->desc.data_std, e->gy2.p);
+  launch_gemm(e->st, e->gy2.p, D, e->d_F1raw, e->gy1.p, D, g.n_own, D, D, nullptr, nullptr, 0, false);
+  launch_dsilu_mul(e->st, (int64_t)g.n_own * D, e->y1p.p, e->gy1.p);
+  launch_gemm(e->st, e->gy1.p, D, e->d_F0raw, e->gx.p, D, g.n_own, D, D, nullptr, nullptr, 0, false);
+  atom_layer_bwd(e, nb - 1);
+  for (int l = nb - 2; l >= 0; l--) {
+    const BondLayerW& w = e->bw[l];
+    if (l < nb - 2) {
+      line_projections(e, l, false);
+      LineArgs a = line_args(e, l, false);
+      line_bwd_common(e, l, false, a);
+      halo_backward(e, e->gh.p, true);
+    }
+    launch_bond_update_bwd(e->st, g.B_own, g.b_vec.p, e->rp3, e->d_W3bw, e->gh.p, e->upd[l].p, e->gupd.p, e->gdb.p);
+    launch_gemm(e->st, e->gupd.p, D, w.Wout_raw, e->gaggB.p, D, g.B_own, D, D, nullptr, nullptr, 0, false);
+    line_projections(e, l, true);
+    LineArgs a = line_args(e, l, true);
+    a.gaggB = e->gaggB.p;
+    line_bwd_common(e, l, true, a);
+    halo_backward(e, e->gx.p, false);
+    atom_layer_bwd(e, l);
+  }
+  // geometry: h0 = W_be be(d_b), theta/Fourier, then edges -> forces and virial
+  launch_h0_bwd(e->st, g.B_loc, g.b_vec.p, e->rp2, e->d_Wbe, e->gh.p, e->gdb.p);
+  launch_angle_init_bwd(e->st, g.A, g.a_in.p, g.a_out.p, g.b_vec.p, e->d_fa, e->d_Wae, e->gang.p, e->gbvec.p);
+  launch_edge_final(e->st, g.E, g.e_src.p, g.e_dst.p, g.e_bond.p, g.e_vec.p, g.gid.p, e->gd.p, e->gdb.p, e->gbvec.p,
+                    e->forces.p, e->scal.p + 1);
+  launch_halo_bond_final(e->st, g.B_own, g.B_loc, g.b_src_gid.p, g.b_dst.p, g.b_vec.p, g.gid.p, e->gdb.p, e->gbvec.p,
+                         e->forces.p, e->scal.p + 1);
+}
+
+static void run(b2m_engine* e, bool grads) {
+  B2M_REQUIRE(e->finalized, B2M_ERR_STATE, "weights not finalized");
+  B2M_REQUIRE(e->have_graph, B2M_ERR_STATE, "b2m_set_structure has not been called");
+  for (auto& p : e->gather_ev) {
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  e->gather_ev.clear();
+  const long long l0 = g_launch_count;
+  B2M_CK(cudaEventRecord(e->ev[0], e->st));
+  forward(e);
+  B2M_CK(cudaEventRecord(e->ev[1], e->st));
+  if (grads) backward(e);
+  if (e->world > 1) {
+    NCCL_CK(g_nccl.AllReduce(e->scal.p, e->scal.p, 10, ncclFloat64, ncclSum, e->comm, e->st));
+    if (grads)
+      NCCL_CK(g_nccl.AllReduce(e->forces.p, e->forces.p, (size_t)e->g.N * 3, ncclFloat32, ncclSum, e->comm, e->st));
+  }
+  B2M_CK(cudaEventRecord(e->ev[2], e->st));
+  B2M_CK(cudaStreamSynchronize(e->st));
+  e->launches_last = g_launch_count - l0;
+  float ms;
+  B2M_CK(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+  e->t_fwd = ms;
+  B2M_CK(cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]));
+  e->t_bwd = ms;
+  double tg = 0;
+  for (auto& p : e->gather_ev) {
+    B2M_CK(cudaEventElapsedTime(&ms, p.first, p.second));
+    tg += ms;
+  }
+  e->t_gather = e->gather_ev.empty() ? 0 : tg / e->gather_ev.size();
+  e->t_total = e->t_fwd + e->t_bwd;
+}
+
+static void fetch(b2m_engine* e, double* energy, float* forces, float* stress9) {
+  double hs[10];
+  B2M_CK(cudaMemcpyAsync(hs, e->scal.p, 10 * sizeof(double), cudaMemcpyDeviceToHost, e->st));
+  if (forces)
+    B2M_CK(cudaMemcpyAsync(forces, e->forces.p, (size_t)e->g.N * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  B2M_CK(cudaStreamSynchronize(e->st));
+  e->last_energy = hs[0] + e->desc.data_mean;
+  if (energy) *energy = e->last_energy;
+  if (stress9)
+    for (int k = 0; k < 9; k++) stress9[k] = (float)(hs[1 + k] / e->g.volume * 160.21766208);  // pes.py:140-145
+}
+
+}  // namespace b2m
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+#define API_BEGIN                               \
+  if (!h) return B2M_ERR_INVALID;               \
+  try {                                         \
+    cudaSetDevice(h->device);
+#define API_END                                 \
+  }                                             \
+  catch (const b2m::Error& ex) {                \
+    h->err = ex.what();                         \
+    return ex.code;                             \
+  }                                             \
+  catch (const std::exception& ex) {            \
+    h->err = ex.what();                         \
+    return B2M_ERR_INVALID;                     \
+  }                                             \
+  return B2M_OK;
+
+static std::string g_create_err;
+
+extern "C" {
+
+int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_handle* out) {
+  if (!desc || !devices || !out) return B2M_ERR_INVALID;
+  try {
+    B2M_REQUIRE(ndev == 1, B2M_ERR_INVALID, "one process per GPU: ndev must be 1 (use b2m_comm_init for world > 1)");
+    B2M_REQUIRE(desc->dim == D && desc->max_n == NR && desc->max_f == 4, B2M_ERR_INVALID,
+                "engine supports dim=64, max_n=9, max_f=4");
+    B2M_REQUIRE(desc->n_blocks >= 2 && desc->n_blocks <= 16, B2M_ERR_INVALID, "n_blocks must be in [2,16]");
+    B2M_REQUIRE(desc->cutoff > 0 && desc->three_body_cutoff > 0 && desc->three_body_cutoff <= desc->cutoff,
+                B2M_ERR_INVALID, "bond_r cannot be greater than regular cutoff");
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count <= 0)
+      throw Error(B2M_ERR_CUDA, std::string("no CUDA device available (libb200mlip has no CPU fallback): ") +
+                                    cudaGetErrorString(ce));
+    B2M_REQUIRE(devices[0] >= 0 && devices[0] < count, B2M_ERR_INVALID, "bad device ordinal");
+    b2m_engine* e = new b2m_engine();
+    e->desc = *desc;
+    e->device = devices[0];
+    B2M_CK(cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    B2M_CK(cudaGetDeviceProperties(&prop, e->device));
+    if (prop.major != 10) {
+      delete e;
+      throw Error(B2M_ERR_CUDA, "libb200mlip is built for sm_100a (B200) only");
+    }
+    B2M_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    for (auto& ev : e->ev) B2M_CK(cudaEventCreate(&ev));
+    *out = e;
+  } catch (const b2m::Error& ex) {
+    g_create_err = ex.what();
+    return ex.code;
+  }
+  return B2M_OK;
+}
+
+int b2m_destroy(b2m_handle h) {
+  if (!h) return B2M_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (auto& p : h->gather_ev) {
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return B2M_OK;
+}
+
+const char* b2m_last_error(b2m_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int b2m_load_weights(b2m_handle h, const char* name, const float* host_ptr, const int64_t* shape, int ndim) {
+  API_BEGIN
+  B2M_REQUIRE(name && host_ptr && shape && ndim >= 1 && ndim <= 4, B2M_ERR_INVALID, "bad weight arguments");
+  size_t n = 1;
+  std::vector<int64_t> sh(shape, shape + ndim);
+  for (auto s : sh) n *= (size_t)s;
+  h->host_w[name] = std::vector<float>(host_ptr, host_ptr + n);
+  h->host_shape[name] = sh;
+  h->finalized = false;
+  API_END
+}
+
+int b2m_set_element_refs(b2m_handle h, const double* offsets, int n) {
+  API_BEGIN
+  B2M_REQUIRE(offsets && n == h->desc.n_elem, B2M_ERR_INVALID, "element_refs length must equal n_elem");
+  h->elem_refs.assign(offsets, offsets + n);
+  h->finalized = false;
+  API_END
+}
+
+int b2m_set_scaling(b2m_handle h, double data_mean, double data_std) {
+  API_BEGIN
+  h->desc.data_mean = data_mean;
+  h->desc.data_std = data_std;
+  API_END
+}
+
+int b2m_finalize_weights(b2m_handle h) {
+  API_BEGIN
+  finalize_weights(h);
+  API_END
+}
+
+int b2m_comm_unique_id(char* out128) {
+  if (!out128) return B2M_ERR_INVALID;
+  try {
+    g_nccl.load();
+    ncclUniqueId id;
+    NCCL_CK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId size");
+    memcpy(out128, &id, 128);
+  } catch (const b2m::Error& ex) {
+    g_create_err = ex.what();
+    return ex.code;
+  }
+  return B2M_OK;
+}
+
+int b2m_comm_init(b2m_handle h, const char* id128, int rank, int world) {
+  API_BEGIN
+  B2M_REQUIRE(world >= 1 && world <= MAXP && rank >= 0 && rank < world, B2M_ERR_PARTITIONS, "bad rank/world");
+  h->rank = rank;
+  h->world = world;
+  if (world > 1) {
+    B2M_REQUIRE(id128 != nullptr, B2M_ERR_INVALID, "unique id required");
+    g_nccl.load();
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCCL_CK(g_nccl.CommInitRank(&h->comm, world, id, rank));
+  }
+  API_END
+}
+
+int b2m_set_structure(b2m_handle h, int64_t natoms, const double* cart, const double* lattice9,
+                      const int32_t* species, const int* pbc3, double tol) {
+  API_BEGIN
+  B2M_REQUIRE(cart && lattice9 && species && pbc3, B2M_ERR_INVALID, "null structure argument");
+  h->have_graph = false;
+  B2M_CK(cudaEventRecord(h->ev[3], h->st));
+  h->g.build(h->st, natoms, cart, lattice9, species, pbc3, h->desc.cutoff, h->desc.three_body_cutoff, tol, h->rank,
+             h->world);
+  alloc_workspace(h);
+  B2M_CK(cudaEventRecord(h->ev[4], h->st));
+  B2M_CK(cudaStreamSynchronize(h->st));
+  float ms;
+  B2M_CK(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
+  h->t_graph = ms;
+  h->have_graph = true;
+  API_END
+}
+
+int b2m_compute(b2m_handle h, int want_forces, int want_stress, double* energy, float* forces, float* stress9) {
+  API_BEGIN
+  run(h, want_forces || want_stress);
+  fetch(h, energy, want_forces ? forces : nullptr, want_stress ? stress9 : nullptr);
+  API_END
+}
+
+int b2m_compute_resident(b2m_handle h, int want_forces, int want_stress, int reps, double* energy, float* ms) {
+  API_BEGIN
+  B2M_REQUIRE(reps >= 1, B2M_ERR_INVALID, "reps >= 1");
+  for (int r = 0; r < reps; r++) run(h, want_forces || want_stress);
+  fetch(h, energy, nullptr, nullptr);
+  if (ms) *ms = (float)h->t_total;
+  API_END
+}
+
+int b2m_get_sitewise(b2m_handle h, float* out) {
+  API_BEGIN
+  B2M_REQUIRE(h->have_graph && out, B2M_ERR_STATE, "no structure");
+  Graph& g = h->g;
+  std::vector<float> loc(g.n_own);
+  std::vector<int> gid(g.n_own);
+  B2M_CK(cudaMemcpyAsync(loc.data(), h->site.p, g.n_own * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+  B2M_CK(cudaMemcpyAsync(gid.data(), g.gid.p, g.n_own * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  B2M_CK(cudaStreamSynchronize(h->st));
+  std::vector<float> full(g.N, 0.f);
+  for (int i = 0; i < g.n_own; i++) full[gid[i]] = loc[i];
+  if (h->world > 1) {
+    B2M_CK(cudaMemcpyAsync(h->site_full.p, full.data(), g.N * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    NCCL_CK(g_nccl.AllReduce(h->site_full.p, h->site_full.p, (size_t)g.N, ncclFloat32, ncclSum, h->comm, h->st));
+    B2M_CK(cudaMemcpyAsync(full.data(), h->site_full.p, g.N * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    B2M_CK(cudaStreamSynchronize(h->st));
+  }
+  memcpy(out, full.data(), g.N * sizeof(float));
+  API_END
+}
+
+int b2m_get_counts(b2m_handle h, int64_t* out, int n) {
+  API_BEGIN
+  B2M_REQUIRE(out && n >= 10, B2M_ERR_INVALID, "need room for 10 counts");
+  Graph& g = h->g;
+  out[0] = g.n_own, out[1] = g.n_halo, out[2] = g.E, out[3] = g.B_own, out[4] = g.B_halo, out[5] = g.A;
+  out[6] = g.axis, out[7] = h->rank, out[8] = h->world, out[9] = h->launches_last;
+  API_END
+}
+
+int64_t b2m_get_partition_info(b2m_handle h, int which, int64_t* out, int64_t cap) {
+  if (!h) return B2M_ERR_INVALID;
+  try {
+    cudaSetDevice(h->device);
+    B2M_REQUIRE(h->have_graph && out, B2M_ERR_STATE, "no structure");
+    return h->g.export_info(h->st, which, out, cap);
+  } catch (const b2m::Error& ex) {
+    h->err = ex.what();
+    return ex.code;
+  }
+}
+
+int b2m_debug_tensor(b2m_handle h, const char* name, float* out, int64_t cap, int64_t* rows, int64_t* cols) {
+  API_BEGIN
+  B2M_REQUIRE(h->have_graph && name && out && rows && cols, B2M_ERR_STATE, "no structure");
+  Graph& g = h->g;
+  std::string n(name);
+  const float* src = nullptr;
+  int64_t r = 0, c = D;
+  auto idx = [&](const std::string& pre) { return atoi(n.c_str() + pre.size()); };
+  if (n[0] == 'x' && isdigit(n[1])) {
+    int l = idx("x");
+    B2M_REQUIRE(l >= 0 && l < (int)h->x.size(), B2M_ERR_INVALID, "bad layer");
+    src = h->x[l].p, r = l == (int)h->x.size() - 1 ? g.n_own : g.n_loc;
+  } else if (n[0] == 'h' && isdigit(n[1])) {
+    int l = idx("h");
+    B2M_REQUIRE(l >= 0 && l < (int)h->h.size(), B2M_ERR_INVALID, "bad layer");
+    src = h->h[l].p, r = g.B_own;
+  } else if (n.rfind("ang", 0) == 0 && isdigit(n[3])) {
+    int l = idx("ang");
+    B2M_REQUIRE(l >= 0 && l < (int)h->ang.size(), B2M_ERR_INVALID, "bad layer");
+    src = h->ang[l].p, r = g.A;
+  } else if (n == "e_atom") {
+    src = h->e_atom.p, r = g.n_own, c = 1;
+  } else if (n == "gd") {
+    src = h->gd.p, r = g.E, c = 1;
+  } else if (n == "gdb") {
+    src = h->gdb.p, r = g.B_loc, c = 1;
+  } else if (n == "gbvec") {
+    src = h->gbvec.p, r = g.B_loc, c = 3;
+  } else if (n == "gx") {
+    src = h->gx.p, r = g.n_loc;
+  } else if (n == "gh") {
+    src = h->gh.p, r = g.B_loc;
+  } else if (n == "gang") {
+    src = h->gang.p, r = g.A;
+  } else if (n == "e_vec") {
+    src = reinterpret_cast<const float*>(g.e_vec.p), r = g.E, c = 4;
+  } else {
+    throw Error(B2M_ERR_INVALID, "unknown debug tensor: " + n);
+  }
+  B2M_REQUIRE(r * c <= cap, B2M_ERR_INVALID, "debug buffer too small");
+  B2M_CK(cudaMemcpyAsync(out, src, r * c * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+  B2M_CK(cudaStreamSynchronize(h->st));
+  *rows = r, *cols = c;
+  API_END
+}
+
+int b2m_last_timings(b2m_handle h, double* out, int n) {
+  API_BEGIN
+  B2M_REQUIRE(out && n >= 5, B2M_ERR_INVALID, "need room for 5 timings");
+  out[0] = h->t_graph, out[1] = h->t_fwd, out[2] = h->t_bwd, out[3] = h->t_gather, out[4] = h->t_total;
+  API_END
+}
+
+}  // extern "C"

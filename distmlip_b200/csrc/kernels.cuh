@@ -1,0 +1,128 @@
+// kernels.cuh -- launch-side declarations of the CHGNet hot-path kernels (sm_100a).
+//
+// Formulation (verified against autograd in oracle/manual_ref.py):
+//   first layer of every GatedMLP is split by input block, so the per-edge / per-angle work is
+//     pre = gather(node projections) + (rank-9 radial term | dense 64->128 on the row's own feature)
+//   followed by the 64x64 second layers, the gate product and a segmented sum.
+// Reference arithmetic being replaced: SURVEY.md 8 rows a6-a15 (DistMLIP chgnet.py:208-453,
+// chgnet_layers.py:16-119; matgl layer internals restated in SURVEY.md 9).
+#pragma once
+#include "common.cuh"
+
+namespace b2m {
+
+constexpr int TM = 128;   // rows (edges / angles) per tile
+constexpr int LD = 132;   // smem row pitch of a [TM][128] tile (16B aligned, 4-bank skew)
+constexpr int LDA = 68;   // smem row pitch of a [TM][64] tile
+constexpr int NT = 256;   // threads per block for the fused tile kernels
+
+struct RadialParams {
+  float freq[NR];
+  float rc;
+  float norm;  // sqrt(2/rc)
+  int p;
+};
+
+// -------- generic row GEMM: C[M,N] = (R | accum C | 0) + A[M,K] @ B[K,N] + bias --------
+void launch_gemm(cudaStream_t st, const float* A, int lda, const float* B, float* C, int ldc, int M, int N, int K,
+                 const float* bias, const float* R, int ldr, bool accum);
+
+// -------- elementwise / init --------
+void launch_embed(cudaStream_t st, int n, const int* type, const float* emb, float* x0);
+void launch_bond_init(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp, const float* W /*[64][9]*/,
+                      float* out /*[nb,64]*/);
+void launch_angle_init(cudaStream_t st, int64_t na, const int* a_in, const int* a_out, const float4* b_vec,
+                       const float* fa /*[5]*/, const float* Wae /*[64][9]*/, float* ang0);
+void launch_silu(cudaStream_t st, int64_t n, const float* pre, float* out);
+void launch_dsilu_mul(cudaStream_t st, int64_t n, const float* pre, float* g);  // g *= dsilu(pre)
+void launch_zero_rows(cudaStream_t st, float* p, int64_t nfloats);
+
+// -------- atom conv (the edge-gather kernel of the headline metric) --------
+struct AtomConvArgs {
+  int64_t E;
+  const int* e_src;
+  const int* e_dst;
+  const int* e_bond;
+  const float4* e_vec;
+  const float* Aproj;  // [n_loc,128]  x @ W1s^T
+  const float* Cproj;  // [n_own,128]  x @ W1t^T + b1
+  const float* Qproj;  // [B_own,128]  h @ W1e^T   (nullptr for layer 0)
+  const float* M;      // [128][9]     W1e @ W_be
+  const float* W2k;    // [2][64][64]  k-major second layers (L then G)
+  const float* W2raw;  // [2][64][64]  as stored [out][in] (backward)
+  const float* b2;     // [128]
+  const float* Wabw;   // [64][9]
+  RadialParams rp;
+  // forward
+  float* agg;  // [n_own,64] (+=)
+  // backward
+  const float* gagg;  // [n_own,64]
+  float* gA;          // [n_loc,128] (+=, atomics)   nullptr -> skip (layer 0)
+  float* gC;          // [n_own,128] (+=)
+  float* gQ;          // [B_own,128] (=)
+  float* gd;          // [E] (+=)
+};
+void launch_atomconv_fwd(cudaStream_t st, const AtomConvArgs& a);
+void launch_atomconv_bwd(cudaStream_t st, const AtomConvArgs& a);
+
+// -------- bond conv ("node" phase, HIDDEN) and angle update ("edge" phase, !HIDDEN) --------
+struct LineArgs {
+  int64_t A;
+  const int* a_in;
+  const int* a_out;
+  const int* a_ctr;
+  const float* ang;   // [A,64] input angle features
+  const float* Ha;    // [B_loc,128]
+  const float* Hb;    // [B_own,128] (+bias folded)
+  const float* Xc;    // [n_loc,128]
+  const float* Wgk;   // [2][64][64] k-major angle block of the first layer
+  const float* Wgraw; // [128][64]   as stored (backward)
+  const float* W2k;   // hidden only
+  const float* W2raw;
+  const float* b2;
+  // forward outputs
+  float* aggB;     // HIDDEN: [B_own,64] (+=)
+  float* ang_out;  // !HIDDEN: [A,64]
+  // backward
+  const float* gaggB;  // HIDDEN: [B_own,64]
+  float* gang;         // [A,64]: !HIDDEN reads it as upstream grad; both accumulate into it
+  float* gHa;          // [B_loc,128] (+=)
+  float* gHb;          // [B_own,128] (+=)
+  float* gXc;          // [n_loc,128] (+=)
+};
+void launch_line_fwd(cudaStream_t st, const LineArgs& a, bool hidden);
+void launch_line_bwd(cudaStream_t st, const LineArgs& a, bool hidden);
+
+// -------- bond update: h' = h + upd * w3b(d_b) --------
+void launch_bond_update_fwd(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp3, const float* W3bw,
+                            const float* h, const float* upd, float* hout);
+// gupd = gh * w3b ; gdb += sum_k (sum_c gh*upd*W3bw[c][k]) * dtbe_k
+void launch_bond_update_bwd(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp3, const float* W3bw,
+                            const float* gh, const float* upd, float* gupd, float* gdb);
+// gdb += sum_k (sum_c gh0[b][c] Wbe[c][k]) dbe_k(d_b)
+void launch_h0_bwd(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp, const float* Wbe, const float* gh0,
+                   float* gdb);
+// theta / Fourier backward: gbvec[a], gbvec[b] += ...
+void launch_angle_init_bwd(cudaStream_t st, int64_t na, const int* a_in, const int* a_out, const float4* b_vec,
+                           const float* fa, const float* Wae, const float* gang0, float* gbvec);
+
+// -------- readout --------
+// e_atom = y2 @ F2 + c2 (+elem ref); energy (double) += sum; site = x @ Ws + bs
+void launch_rowdot(cudaStream_t st, int n, const float* X, const float* w, float bias, float* out, double* sum,
+                   const int* type, const float* elem_ref, float scale);
+// g[r][c] = scale * w[c] * dsilu(pre[r][c])
+void launch_readout_seed(cudaStream_t st, int n, const float* pre, const float* w, float scale, float* g);
+
+// -------- final geometry backward --------
+void launch_edge_final(cudaStream_t st, int64_t E, const int* e_src, const int* e_dst, const int* e_bond,
+                       const float4* e_vec, const int* gid, const float* gd, const float* gdb, const float* gbvec,
+                       float* forces /*[N,3]*/, double* virial /*[9]*/);
+void launch_halo_bond_final(cudaStream_t st, int b0, int b1, const int* b_src_gid, const int* b_dst,
+                            const float4* b_vec, const int* gid, const float* gdb, const float* gbvec, float* forces,
+                            double* virial);
+
+// -------- halo pack / unpack --------
+void launch_gather_rows(cudaStream_t st, int n, int width, const int* idx, const float* src, float* dst);
+void launch_scatter_add_rows(cudaStream_t st, int n, int width, const int* idx, const float* src, float* dst);
+
+}  // namespace b2m

@@ -1,0 +1,140 @@
+"""CHGNet_Dist -- drop-in for DistMLIP.implementations.matgl.models.chgnet.CHGNet_Dist.
+
+Same public surface (`from_existing`, `enable_distributed_mode`, `potential_forward_dist`), but the
+forward/backward run in libb200mlip.so (hand-written sm_100a kernels) instead of PyTorch + DGL:
+
+  reference                                                    here
+  ---------------------------------------------------------    ------------------------------------------
+  from_existing: shallow __dict__ copy   (chgnet.py:551-560)   same, plus a state_dict snapshot
+  enable_distributed_mode: deep-copy 13 sub-modules per GPU    b2m_create + b2m_load_weights (one process
+    from one Python thread               (chgnet.py:455-549)     per GPU; weights replicated, never sharded)
+  potential_forward_dist + dist_forward  (chgnet.py:21-453)    b2m_compute on the resident graph
+
+One process per GPU: under `torchrun` (torch.distributed initialised, world == len(gpus)) rank r
+drives gpus[r]; a single process may only pass one GPU.  "cpu" entries are rejected: there is no
+CPU path in this engine.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+import distmlip_b200
+from distmlip_b200 import _lib
+
+
+class CHGNet_Dist:
+    """Main CHGNet model (B200 engine behind the reference's wrapper API)."""
+
+    __version__ = 1
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_existing(cls, model, dtype=distmlip_b200.float_th):
+        """chgnet.py:551-560: takes a matgl `CHGNet` (any nn.Module with that attribute tree)."""
+        if dtype not in (torch.float, torch.float32):
+            raise ValueError("the sm_100a engine computes in fp32 only")
+        model.to("cpu")
+        dist_model = cls.__new__(cls)
+        dist_model.__dict__ = model.__dict__.copy()
+        dist_model._state_dict = {k: v.detach().clone().float() for k, v in model.state_dict().items()}
+        dist_model.dist_enabled = False
+        dist_model.dtype = dtype
+        dist_model._engine = None
+        return dist_model
+
+    def _attr(self, name, default=None):
+        # nn.Module keeps sub-modules/buffers out of __dict__'s top level; plain attributes are there.
+        if name in self.__dict__:
+            return self.__dict__[name]
+        for store in ("_modules", "_parameters", "_buffers"):
+            d = self.__dict__.get(store)
+            if d is not None and name in d:
+                return d[name]
+        return default
+
+    def __getattr__(self, name):
+        v = self._attr(name, default=AttributeError)
+        if v is AttributeError:
+            raise AttributeError(name)
+        return v
+
+    def enable_distributed_mode(self, gpus):
+        """chgnet.py:455-549. `gpus`: CUDA ordinals, one per partition."""
+        if self.__dict__.get("dist_enabled"):
+            raise Exception("Current model already has distributed mode enabled.")
+        gpus = list(gpus)
+        if any(g == "cpu" for g in gpus):
+            raise RuntimeError('"cpu" partitions are not supported: libb200mlip has no CPU fallback')
+        if len(gpus) < 1:
+            raise ValueError("need at least one GPU")
+        rank, world = 0, 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        if world != len(gpus):
+            if len(gpus) == 1 and world >= 1:
+                rank, world = 0, 1  # replica mode: every process runs its own single-GPU engine
+            else:
+                raise RuntimeError(
+                    f"enable_distributed_mode({gpus}) needs one process per GPU: launch with "
+                    f"`torchrun --nproc-per-node {len(gpus)}` (torch.distributed world is {world})")
+        self.gpus = ["cuda:" + str(g) for g in gpus]
+        sd = self._state_dict
+        dim = int(sd["atom_embedding.weight"].shape[1])
+        max_n = int(sd["bond_expansion.frequencies"].shape[0])
+        max_f = int(sd["angle_expansion.frequencies"].shape[0]) - 1
+        if not self._attr("use_bond_graph", True):
+            raise NotImplementedError("use_bond_graph=False is not supported by the engine yet")
+        if self._attr("state_embedding") is not None:
+            raise NotImplementedError("State features not implemented for distributed computation.")
+        if self._attr("readout_field", "atom_feat") not in ("atom_feat", "node_feat"):
+            raise NotImplementedError("only atom_feat readout is supported (chgnet.py:442-449)")
+        eng = _lib.Engine(
+            n_elem=int(sd["atom_embedding.weight"].shape[0]), dim=dim, max_n=max_n, max_f=max_f,
+            n_blocks=int(self._attr("n_blocks")), cutoff=float(self._attr("cutoff")),
+            three_body_cutoff=float(self._attr("three_body_cutoff")),
+            cutoff_exponent=int(self._attr("cutoff_exponent")), device=int(gpus[rank]))
+        eng.load_state_dict(sd)
+        if world > 1:
+            ids = [_lib.comm_unique_id() if rank == 0 else None]
+            torch.distributed.broadcast_object_list(ids, src=0)
+            eng.comm_init(ids[0], rank, world)
+        self._engine = eng
+        self._engine_finalized = False
+        self._rank, self._world = rank, world
+        self.element_to_index = {elem: idx for idx, elem in enumerate(self._attr("element_types"))}
+        self.dist_enabled = True
+
+    # ------------------------------------------------------------------ hot path
+    def _finalize(self, data_mean, data_std, element_refs):
+        eng = self._engine
+        key = (float(data_mean), float(data_std), None if element_refs is None else tuple(np.ravel(element_refs)))
+        if self._engine_finalized and key == self._final_key:
+            return
+        eng.set_scaling(key[0], key[1])
+        if element_refs is not None:
+            eng.set_element_refs(np.ravel(element_refs))
+        eng.finalize()
+        self._engine_finalized, self._final_key = True, key
+
+    def potential_forward_dist(self, dist_info, atoms, lattice_matrix, calc_stresses, calc_forces, calc_hessian,
+                               state_attr=None):
+        """Seam of chgnet.py:21-30,199-206.  Returns (node_types, positions, strain, (E, site_wise));
+        forces / stress of the same evaluation are left on `dist_info` (no autograd graph exists)."""
+        if calc_hessian:
+            raise NotImplementedError("Calculating hessians is not implemented for distributed inference.")
+        eng = self._engine
+        e, f, s = eng.compute(forces=calc_forces, stress=calc_stresses)
+        dist_info.forces, dist_info.stress = f, s
+        node_types = torch.as_tensor(dist_info.species, dtype=distmlip_b200.int_th)
+        positions = torch.as_tensor(np.asarray(atoms.get_positions(wrap=False)), dtype=distmlip_b200.float_th)
+        strain = torch.zeros(1, 3, 3, dtype=distmlip_b200.float_th)
+        site = torch.as_tensor(eng.sitewise()).reshape(-1, 1)
+        return node_types, positions, strain, (torch.tensor([e], dtype=torch.float64), site)
+
+    def dist_forward(self, *args, **kwargs):
+        raise NotImplementedError("dist_forward over DGL graphs does not exist here; use potential_forward_dist")
+
+    def predict_structure_dist(self, structure, state_feats=None):
+        raise NotImplementedError(
+            "Distributed direct property prediction is not yet supported. Please raise an issue or use Potential_Dist")
