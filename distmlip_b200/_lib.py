@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libb200mlip.so")
 
 SYMBOLS = [
     "b2m_create", "b2m_destroy", "b2m_last_error", "b2m_load_weights", "b2m_set_element_refs",
-    "b2m_finalize_weights", "b2m_set_scaling", "b2m_comm_unique_id", "b2m_comm_init", "b2m_set_structure", "b2m_compute",
+    "b2m_finalize_weights", "b2m_set_scaling", "b2m_comm_unique_id", "b2m_comm_init", "b2m_set_partition", "b2m_set_structure", "b2m_compute",
     "b2m_compute_resident", "b2m_get_sitewise", "b2m_get_counts", "b2m_get_partition_info",
     "b2m_debug_tensor", "b2m_last_timings",
 ]
@@ -61,6 +61,7 @@ def load_library():
     lib.b2m_set_scaling.argtypes = [vp, dbl, dbl]
     lib.b2m_comm_unique_id.argtypes = [C.c_char_p]
     lib.b2m_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
+    lib.b2m_set_partition.argtypes = [vp, i32, i32]
     lib.b2m_set_structure.argtypes = [vp, i64, P(dbl), P(dbl), P(C.c_int32), P(C.c_int), dbl]
     lib.b2m_compute.argtypes = [vp, i32, i32, P(dbl), P(C.c_float), P(C.c_float)]
     lib.b2m_compute_resident.argtypes = [vp, i32, i32, i32, P(dbl), P(C.c_float)]
@@ -139,6 +140,10 @@ class Engine:
 
     def comm_init(self, unique_id: bytes | None, rank: int, world: int):
         self._ck(self.lib.b2m_comm_init(self.h, unique_id, rank, world))
+        self.rank, self.world = rank, world
+
+    def set_partition(self, rank: int, world: int):
+        self._ck(self.lib.b2m_set_partition(self.h, rank, world))
         self.rank, self.world = rank, world
 
     # ---- structure / compute ----

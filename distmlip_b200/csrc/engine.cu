@@ -597,6 +597,8 @@ static void backward(b2m_engine* e) {
 static void run(b2m_engine* e, bool grads) {
   B2M_REQUIRE(e->finalized, B2M_ERR_STATE, "weights not finalized");
   B2M_REQUIRE(e->have_graph, B2M_ERR_STATE, "b2m_set_structure has not been called");
+  B2M_REQUIRE(e->world == 1 || e->comm != nullptr, B2M_ERR_STATE,
+              "world > 1 without a communicator (b2m_set_partition is a graph-only view)");
   for (auto& p : e->gather_ev) {
     cudaEventDestroy(p.first);
     cudaEventDestroy(p.second);
@@ -778,6 +780,16 @@ int b2m_comm_init(b2m_handle h, const char* id128, int rank, int world) {
     memcpy(&id, id128, 128);
     NCCL_CK(g_nccl.CommInitRank(&h->comm, world, id, rank));
   }
+  API_END
+}
+
+int b2m_set_partition(b2m_handle h, int rank, int world) {
+  API_BEGIN
+  B2M_REQUIRE(world >= 1 && world <= MAXP && rank >= 0 && rank < world, B2M_ERR_PARTITIONS, "bad rank/world");
+  B2M_REQUIRE(h->comm == nullptr, B2M_ERR_STATE, "communicator already initialised");
+  h->rank = rank;
+  h->world = world;
+  h->have_graph = false;
   API_END
 }
 

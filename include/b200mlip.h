@@ -80,6 +80,9 @@ int b2m_finalize_weights(b2m_handle h);
 /* Multi-process graph parallelism: rank 0 makes an id, every rank calls b2m_comm_init with it. */
 int b2m_comm_unique_id(char* out128);
 int b2m_comm_init(b2m_handle h, const char* id128, int rank, int world);
+/* Graph-only view of partition `rank` of `world` without a communicator (parity tests of the
+ * partitioner on one GPU).  b2m_compute refuses to run in this state when world > 1. */
+int b2m_set_partition(b2m_handle h, int rank, int world);
 
 /* Graph build (neighbour list, slab partition, halo sections, bond graph, angles) on the GPU.
  * cart: [natoms,3] f64 Cartesian (unwrapped ok); lattice9: row vectors; species: index into

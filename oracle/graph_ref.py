@@ -91,13 +91,16 @@ def neighbor_list(cart, lattice, pbc, r, bond_r, tol=1e-8):
     # image range: enough images that every point within r of any centre is present
     recip = np.linalg.inv(lattice).T  # rows = reciprocal vectors / 2pi
     heights = 1.0 / np.linalg.norm(recip, axis=1)
-    nimg = [int(np.ceil((r + 1e-6) / h)) + 1 if pbc[k] else 0 for k, h in enumerate(heights)]
+    # image range must reach the (possibly unwrapped) centres: fpis.c get_bounds(:489-491)
+    frac_c = wrapped + corr
+    ilo = [int(np.floor(frac_c[:, k].min() - (r + 1e-6) / h)) - 1 if pbc[k] else 0 for k, h in enumerate(heights)]
+    ihi = [int(np.ceil(frac_c[:, k].max() + (r + 1e-6) / h)) + 1 if pbc[k] else 0 for k, h in enumerate(heights)]
     lo = cart.min(axis=0) - r - 1e-6
     hi = cart.max(axis=0) + r + 1e-6
     pts, idx, img = [], [], []
-    for a in range(-nimg[0], nimg[0] + 1):
-        for b in range(-nimg[1], nimg[1] + 1):
-            for c in range(-nimg[2], nimg[2] + 1):
+    for a in range(ilo[0], ihi[0] + 1):
+        for b in range(ilo[1], ihi[1] + 1):
+            for c in range(ilo[2], ihi[2] + 1):
                 shift = a * lattice[0] + b * lattice[1] + c * lattice[2]
                 p = wc + shift
                 m = np.all((p > lo) & (p < hi), axis=1)

@@ -70,3 +70,72 @@ def manual_run(model, atoms, og, dtype=torch.float64, data_std=1.0):
     types = np.array([model.element_types.index(s) for s in atoms.get_chemical_symbols()])
     return M.run(model, types, og["vec"], og["i1"], og["i2"], og["bond_edges"], og["la"], og["lb"], og["ce"],
                  data_std=data_std, dtype=dtype)
+
+
+# ---- order-independent digests shared with tests/golden/make_golden.py ----
+MOD = (1 << 61) - 1
+
+
+def digest(rows):
+    rows = np.asarray(rows, dtype=np.int64)
+    if rows.size == 0:
+        return [0, 0, 0]
+    rows = rows.reshape(len(rows), -1)
+    acc = np.zeros(len(rows), dtype=object)
+    for c in range(rows.shape[1]):
+        acc = (acc * 1000003 + (rows[:, c].astype(object) + 7919)) % MOD
+    return [int(len(rows)), int(sum(acc) % MOD), int(sum((a * a) % MOD for a in acc) % MOD)]
+
+
+def golden_cases():
+    import importlib.util
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.cases()
+
+
+def oracle_partition_digests(o, p):
+    """same fields as make_golden.describe()['parts'][p], from a GraphOracle"""
+    P = o.P
+    s, d, of = o.edges_of(p)
+    bs, bd, bo = o.bonds_owned(p)
+    hs, _hd, _ho = o.bonds_halo(p)
+    ang = o.angles_of(p)
+    return {
+        "n_owned": int(len(o.owned(p))),
+        "owned": digest(o.owned(p)[:, None]),
+        "to": [digest(o.to_list(p, q)[:, None]) if q != p else [0, 0, 0] for q in range(P)],
+        "from": [digest(o.from_list(p, q)[:, None]) if q != p else [0, 0, 0] for q in range(P)],
+        "edges": digest(np.column_stack([s, d, of])),
+        "bonds_owned": digest(np.column_stack([bs, bd, bo])),
+        "n_bond_halo": int(len(hs)),
+        "n_angles": int(len(ang)),
+        "angle_dst_center": digest(ang[:, [1, 5, 6, 7, 8, 9]]) if len(ang) else [0, 0, 0],
+    }
+
+
+def engine_partition_digests(eng, P):
+    c = eng.counts()
+    own = np.sort(eng.partition_info(0))
+    halo, howner = eng.partition_info(1), eng.partition_info(2)
+    tl = eng.partition_info(6)
+    edges = eng.partition_info(3)
+    bonds = eng.partition_info(4)
+    ang = eng.partition_info(5)
+    nbo = c["n_bond_own"]
+    outb = bonds[ang[:, 1]] if len(ang) else np.zeros((0, 5), dtype=np.int64)
+    return {
+        "n_owned": int(c["n_own"]),
+        "owned": digest(own[:, None]),
+        "to": [digest(np.sort(tl[tl[:, 0] == q, 1])[:, None]) if len(tl) else [0, 0, 0] for q in range(P)],
+        "from": [digest(halo[howner == q][:, None]) for q in range(P)],
+        "edges": digest(edges),
+        "bonds_owned": digest(bonds[:nbo]),
+        "n_bond_halo": int(c["n_bond_halo"]),
+        "n_angles": int(c["n_angles"]),
+        "angle_dst_center": digest(np.column_stack([outb, ang[:, 2]])) if len(ang) else [0, 0, 0],
+    }
