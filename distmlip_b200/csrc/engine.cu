@@ -65,6 +65,7 @@ static Nccl g_nccl;
 // ------------------------------------------------------------------------------------------
 struct AtomLayerW {
   float *W1s_k, *W1e_k, *W1t_k, *b1, *W1s_raw, *W1e_raw, *W1t_raw, *M, *W2k, *W2raw, *b2, *Wout_k, *Wout_raw;
+  float *W2can, *Mcan;  // tcgen05 operands (canonical UMMA layout, tf32 hi/lo planes)
 };
 struct BondLayerW {
   float *W1a_k, *W1b_k, *W1c_k, *Wg_k, *b1, *W1a_raw, *W1b_raw, *W1c_raw, *Wg_raw, *W2k, *W2raw, *b2, *Wout_k, *Wout_raw;
@@ -110,6 +111,8 @@ struct b2m_engine {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gather_ev;
   long long launches_last = 0;
   double last_energy = 0;
+  int num_sms = 148;
+  bool use_tc = true;  // tcgen05 kernels; B2M_LEGACY_FFMA=1 selects the FP32-FFMA tile kernels (A/B checks)
 };
 
 namespace b2m {
@@ -159,6 +162,32 @@ static std::vector<float> branch_kmajor(const std::vector<float>& raw128x64) {
   for (int br = 0; br < 2; br++)
     for (int k = 0; k < 64; k++)
       for (int n = 0; n < 64; n++) o[((size_t)br * 64 + k) * 64 + n] = raw128x64[((size_t)br * 64 + n) * 64 + k];
+  return o;
+}
+
+// tf32 "hi" part: round-to-nearest (ties away) on the 13 dropped mantissa bits == cvt.rna.tf32.f32
+static float tf32_hi_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u += 0x1000u;
+  u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+// raw [N][K] row-major (K contiguous == K-major operand) -> canonical no-swizzle core-matrix layout
+// (8 rows x 16 B per core matrix; K-chunk-major then row-group), hi plane followed by lo plane.
+// element (n, k) at ((k/4) * (N/8) + n/8) * 32 + (n%8)*4 + k%4 ;  Kpad >= K pads with zeros.
+static std::vector<float> canon_split(const std::vector<float>& raw, int N, int K, int Kpad) {
+  std::vector<float> o((size_t)2 * N * Kpad, 0.f);
+  for (int n = 0; n < N; n++)
+    for (int k = 0; k < K; k++) {
+      const size_t off = ((size_t)(k / 4) * (N / 8) + n / 8) * 32 + (n % 8) * 4 + (k % 4);
+      const float x = raw[(size_t)n * K + k];
+      const float h = tf32_hi_host(x);
+      o[off] = h;
+      o[(size_t)N * Kpad + off] = x - h;
+    }
   return o;
 }
 
@@ -230,6 +259,11 @@ static void finalize_weights(b2m_engine* e) {
     put(q + "b2", b2);
     put(q + "Wout_k", transpose(Wout, 64, 64));
     put(q + "Wout_raw", Wout);
+    {
+      const std::vector<float> W2L(W2.begin(), W2.begin() + 4096), W2G(W2.begin() + 4096, W2.end());
+      put(q + "W2can", vcat(canon_split(W2L, 64, 64, 64), canon_split(W2G, 64, 64, 64)));
+      put(q + "Mcan", canon_split(M, 128, 9, 16));
+    }
   }
   for (int l = 0; l < nb - 1; l++) {
     const std::string p = "bond_graph_layers." + std::to_string(l) + ".conv_layer.";
@@ -313,6 +347,7 @@ static void finalize_weights(b2m_engine* e) {
     w.W1s_raw = dp(q + "W1s_raw"), w.W1e_raw = dp(q + "W1e_raw"), w.W1t_raw = dp(q + "W1t_raw");
     w.M = dp(q + "M"), w.W2k = dp(q + "W2k"), w.W2raw = dp(q + "W2raw"), w.b2 = dp(q + "b2");
     w.Wout_k = dp(q + "Wout_k"), w.Wout_raw = dp(q + "Wout_raw");
+    w.W2can = dp(q + "W2can"), w.Mcan = dp(q + "Mcan");
   }
   e->bw.resize(nb - 1);
   for (int l = 0; l < nb - 1; l++) {
@@ -445,7 +480,12 @@ static void atom_layer_fwd(b2m_engine* e, int l) {
   B2M_CK(cudaEventCreate(&e0));
   B2M_CK(cudaEventCreate(&e1));
   B2M_CK(cudaEventRecord(e0, e->st));
-  launch_atomconv_fwd(e->st, a);
+  if (e->use_tc) {
+    AtomConvTcW tw{w.W2can, w.Mcan};
+    launch_atomconv_fwd_tc(e->st, a, tw, e->num_sms);
+  } else {
+    launch_atomconv_fwd(e->st, a);
+  }
   B2M_CK(cudaEventRecord(e1, e->st));
   e->gather_ev.push_back({e0, e1});
   launch_gemm(e->st, e->agg.p, D, w.Wout_k, e->x[l + 1].p, D, g.n_own, D, D, nullptr, e->x[l].p, D, false);
@@ -692,6 +732,11 @@ int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_han
     if (prop.major != 10) {
       delete e;
       throw Error(B2M_ERR_CUDA, "libb200mlip is built for sm_100a (B200) only");
+    }
+    e->num_sms = prop.multiProcessorCount;
+    {
+      const char* leg = getenv("B2M_LEGACY_FFMA");
+      e->use_tc = !(leg && leg[0] == '1');
     }
     B2M_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     for (auto& ev : e->ev) B2M_CK(cudaEventCreate(&ev));

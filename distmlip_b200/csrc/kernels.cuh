@@ -126,3 +126,16 @@ void launch_gather_rows(cudaStream_t st, int n, int width, const int* idx, const
 void launch_scatter_add_rows(cudaStream_t st, int n, int width, const int* idx, const float* src, float* dst);
 
 }  // namespace b2m
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 (5th-gen tensor core) variants.  3xTF32 split (hi*hi + lo*hi + hi*lo, fp32 accumulate in
+// TMEM) keeps fp32-level accuracy.  Weights are pre-formatted on the host into the canonical
+// K-major / no-swizzle core-matrix layout (8 rows x 16 B), hi and lo planes (see engine.cu: canon()).
+// ---------------------------------------------------------------------------------------------
+namespace b2m {
+struct AtomConvTcW {
+  const float* W2can;  // [4][4096]: W2L hi, W2L lo, W2G hi, W2G lo   (N=64, K=64)
+  const float* Mcan;   // [2][2048]: M hi, M lo                        (N=128, K=16; k>=9 zero)
+};
+void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
+}  // namespace b2m

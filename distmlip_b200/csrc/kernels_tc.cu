@@ -1,0 +1,351 @@
+// kernels_tc.cu -- tcgen05 / TMEM versions of the fused tile kernels (sm_100a).
+//
+// Design (atom conv forward, the edge-gather kernel of the headline metric):
+//   * persistent CTAs, 256 threads, 2 CTAs per SM, 256 TMEM columns each: [H operand 128 | D accum 128]
+//   * thread <-> row mapping fixed by TMEM: warp w owns lanes 32*(w%4)..+31, half = w/4 picks 32 of 64 columns
+//   * A operands live in TMEM (tcgen05.st from registers, hi/lo tf32 split) -- no shared-memory A tiles
+//   * B operands (weights) staged ONCE per CTA in shared memory, already in canonical UMMA layout
+//   * first-layer radial term  M.be(d)  : one K=16 MMA chain (N=128)
+//     second layers  hid(64) x W2(64x64): two K=64 chains (N=64), gate product in the epilogue
+//   * segmented sum over destination rows through a shared-memory message tile, RED to HBM on run ends
+#include "kernels.cuh"
+
+namespace b2m {
+
+__device__ __forceinline__ float sigm_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_(float x) { return x * sigm_(x); }
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t tf32_hi_bits(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48)
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// tf32 x tf32 -> f32, A from TMEM, B from smem descriptor, M=128
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
+          "r"(addr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_init_(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = s_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ float ipow_(float x, int n) {
+  float r = 1.f;
+  for (int i = 0; i < n; i++) r *= x;
+  return r;
+}
+__device__ __forceinline__ float rbf_env_val(float d, float freq, const RadialParams& rp) {
+  const float invd = 1.f / d;
+  float s, c;
+  sincosf(d * (freq / rp.rc), &s, &c);
+  const float rbf = rp.norm * s * invd;
+  const int p = rp.p;
+  const float c1 = -(p + 1) * (p + 2) * 0.5f, c2 = (float)(p * (p + 2)), c3 = -p * (p + 1) * 0.5f;
+  const float rho = rbf / rp.rc;
+  const float r0 = ipow_(rho, p), r1 = r0 * rho, r2 = r1 * rho;
+  const float env = 1.f + c1 * r0 + c2 * r1 + c3 * r2;
+  return rbf <= rp.rc ? env * rbf : 0.f;
+}
+
+// instruction descriptors: c=F32, a=b=TF32, K-major, M=128
+constexpr uint32_t kIdescN64 = (1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24);
+constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | (16u << 17) | (8u << 24);
+
+struct FwdTcSmem {
+  // float offsets
+  static constexpr int kBar = 0;               // 4 mbarriers + tmem ptr (64 floats reserved)
+  static constexpr int kW2 = 64;                // 4 x 4096
+  static constexpr int kM = kW2 + 4 * 4096;     // 2 x 2048
+  static constexpr int kMsg = kM + 2 * 2048;    // [64][65] (half tile staging)
+  static constexpr int kBe = kMsg + 64 * 65;    // [128][12]
+  static constexpr int kWab = kBe + 128 * 12;   // 576
+  static constexpr int kB2 = kWab + 576;        // 128
+  static constexpr int kD = kB2 + 128;          // [128]
+  static constexpr int kIdx = kD + 128;         // 3 x 128 ints
+  static constexpr int kTotal = kIdx + 3 * 128;
+  static constexpr size_t bytes = (size_t)kTotal * 4;
+};
+
+__global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a, const AtomConvTcW w) {
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + FwdTcSmem::kBar);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + FwdTcSmem::kBar + 16);
+  float* W2s = smem + FwdTcSmem::kW2;
+  float* Ms = smem + FwdTcSmem::kM;
+  float* msg = smem + FwdTcSmem::kMsg;
+  float* be_s = smem + FwdTcSmem::kBe;
+  float* wabW = smem + FwdTcSmem::kWab;
+  float* b2s = smem + FwdTcSmem::kB2;
+  float* s_d = smem + FwdTcSmem::kD;
+  int* s_src = reinterpret_cast<int*>(smem + FwdTcSmem::kIdx);
+  int* s_dst = s_src + 128;
+  int* s_bond = s_dst + 128;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int r = q * 32 + lane;   // my row (TMEM lane)
+  const int c0 = half * 32;      // my 32 columns inside each 64-wide branch
+  const bool useQ = a.Qproj != nullptr;
+
+  // ---- one-time setup: TMEM, barriers, weights ----
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init_(&mbar[0], 1);
+    mbar_init_(&mbar[1], 1);
+    mbar_init_(&mbar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 4 * 1024; i += 256) reinterpret_cast<float4*>(W2s)[i] = reinterpret_cast<const float4*>(w.W2can)[i];
+  for (int i = tid; i < 2 * 512; i += 256) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
+  for (int i = tid; i < 576; i += 256) wabW[i] = a.Wabw[i];
+  if (tid < 128) b2s[tid] = a.b2[tid];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tptr;
+  const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);  // my lane quarter
+  constexpr uint32_t COL_H = 0, COL_D = 128;
+  const uint32_t w2_addr = s_u32(W2s), m_addr = s_u32(Ms);
+  uint32_t phase = 0;
+
+  const int64_t ntiles = (a.E + 127) / 128;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t e0 = t * 128;
+    const int nvalid = (int)min((int64_t)128, a.E - e0);
+    if (tid < 128) {
+      int src = 0, dst = -1, bond = -1;
+      float d = 1.f;
+      if (tid < nvalid) {
+        const int64_t e = e0 + tid;
+        src = a.e_src[e];
+        dst = a.e_dst[e];
+        bond = a.e_bond[e];
+        d = a.e_vec[e].w;
+      }
+      s_src[tid] = src;
+      s_dst[tid] = dst;
+      s_bond[tid] = bond;
+      s_d[tid] = d;
+    }
+    __syncthreads();
+    {  // radial basis with the reference's envelope-on-value quirk; 9 values per edge, padded to 12
+      const float d = s_d[r];
+      const int k0 = half ? 5 : 0, k1 = half ? 9 : 5;
+      for (int k = k0; k < k1; k++) be_s[r * 12 + k] = r < nvalid ? rbf_env_val(d, a.rp.freq[k], a.rp) : 0.f;
+      if (half) be_s[r * 12 + 9] = be_s[r * 12 + 10] = be_s[r * 12 + 11] = 0.f;
+    }
+    __syncthreads();
+    if (half == 0) {  // be -> TMEM operand (K = 16: 9 values + zero pad), hi in cols 0..15, lo in 16..31
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const float x = k < 12 ? be_s[r * 12 + k] : 0.f;
+        const uint32_t h = tf32_hi_bits(x);
+        hi[k] = h;
+        lo[k] = __float_as_uint(x - __uint_as_float(h));
+      }
+      tmem_st16(tlane + COL_H, hi);
+      tmem_st16(tlane + COL_H + 16, lo);
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {  // GEMM1: D[128 x 128] = be[128 x 16] . M^T    (hi*hi + lo*hi + hi*lo)
+      tc_fence_after();
+      uint32_t acc = 0;
+#pragma unroll
+      for (int term = 0; term < 3; term++) {
+        const uint32_t acol = term == 1 ? 16u : 0u;
+        const uint32_t bsel = m_addr + (term == 2 ? 2048u * 4u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+          umma_ts(tbase + COL_D, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 4096u, 2048u, 128u), kIdescN128, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(&mbar[0]);
+    }
+    const int src = s_src[r], dst = s_dst[r], bond = s_bond[r];
+    const bool valid = r < nvalid;
+    const bool viaQ = useQ && bond >= 0;
+    const float* Arow = a.Aproj + (size_t)src * D2;
+    const float* Crow = a.Cproj + (size_t)(valid ? dst : 0) * D2;
+    const float* Qrow = viaQ ? a.Qproj + (size_t)bond * D2 : nullptr;
+    // ---- first layer epilogue + second layer, branch by branch (0: "layers", 1: "gates") ----
+#pragma unroll 1
+    for (int br = 0; br < 2; br++) {
+      mbar_wait_(&mbar[br], phase);
+      tc_fence_after();
+      const int cb = br * 64 + c0;  // column in the 128-wide first layer
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t v[16], hi[16], lo[16];
+        tmem_ld16(tlane + COL_D + cb + ch * 16, v);
+        tc_wait_ld();
+        float av[16], cv[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float4 x = *reinterpret_cast<const float4*>(Arow + cb + ch * 16 + i * 4);
+          const float4 y = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
+          av[4 * i] = x.x, av[4 * i + 1] = x.y, av[4 * i + 2] = x.z, av[4 * i + 3] = x.w;
+          cv[4 * i] = y.x, cv[4 * i + 1] = y.y, cv[4 * i + 2] = y.z, cv[4 * i + 3] = y.w;
+        }
+        if (viaQ) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float4 x = *reinterpret_cast<const float4*>(Qrow + cb + ch * 16 + i * 4);
+            v[4 * i] = __float_as_uint(x.x), v[4 * i + 1] = __float_as_uint(x.y);
+            v[4 * i + 2] = __float_as_uint(x.z), v[4 * i + 3] = __float_as_uint(x.w);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const float p = __uint_as_float(v[i]) + av[i] + cv[i];
+          const float hval = valid ? silu_(p) : 0.f;
+          const uint32_t h = tf32_hi_bits(hval);
+          hi[i] = h;
+          lo[i] = __float_as_uint(hval - __uint_as_float(h));
+        }
+        tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
+        tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {  // GEMM2 for this branch: D[:, br*64 .. +64] = hid[128 x 64] . W2^T
+        tc_fence_after();
+        uint32_t acc = 0;
+#pragma unroll
+        for (int term = 0; term < 3; term++) {
+          const uint32_t acol = term == 1 ? 64u : 0u;
+          const uint32_t bsel = w2_addr + (uint32_t)(br * 2 + (term == 2 ? 1 : 0)) * 4096u * 4u;
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) {
+            umma_ts(tbase + COL_D + br * 64, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 2048u, 1024u, 128u),
+                    kIdescN64, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&mbar[br + 1]);
+      }
+    }
+    mbar_wait_(&mbar[2], phase);
+    tc_fence_after();
+    phase ^= 1;
+    // ---- gate product, shared weights, segmented sum over dst (two half-tiles through smem) ----
+    float mv[32];
+    {
+      float bek[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) bek[k] = be_s[r * 12 + k];
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t u[16], g[16];
+        tmem_ld16(tlane + COL_D + c0 + ch * 16, u);
+        tmem_ld16(tlane + COL_D + 64 + c0 + ch * 16, g);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int c = c0 + ch * 16 + i;
+          const float oL = silu_(__uint_as_float(u[i]) + b2s[c]);
+          const float oG = sigm_(__uint_as_float(g[i]) + b2s[64 + c]);
+          float wab = 0.f;
+#pragma unroll
+          for (int k = 0; k < 9; k++) wab = fmaf(bek[k], wabW[c * 9 + k], wab);
+          mv[ch * 16 + i] = valid ? oL * oG * wab : 0.f;
+        }
+      }
+    }
+    tc_fence_before();
+#pragma unroll 1
+    for (int hp = 0; hp < 2; hp++) {
+      if ((q >> 1) == hp) {
+        const int rr = r - hp * 64;
+#pragma unroll
+        for (int i = 0; i < 32; i++) msg[rr * 65 + c0 + i] = mv[i];
+      }
+      __syncthreads();
+      {
+        const int c = tid & 63, part = tid >> 6;  // 4 parts x 16 rows
+        float sum = 0.f;
+        int cur = -1;
+        const int rbeg = part * 16;
+        for (int rr = rbeg; rr < rbeg + 16; rr++) {
+          const int k = s_dst[hp * 64 + rr];
+          if (k != cur) {
+            if (cur >= 0) atomicAdd(&a.agg[(size_t)cur * D + c], sum);
+            cur = k;
+            sum = 0.f;
+          }
+          if (k >= 0) sum += msg[rr * 65 + c];
+        }
+        if (cur >= 0) atomicAdd(&a.agg[(size_t)cur * D + c], sum);
+      }
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
+}
+
+void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
+  if (a.E <= 0) return;
+  static bool attr = false;
+  if (!attr) {
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
+    attr = true;
+  }
+  const int64_t ntiles = (a.E + 127) / 128;
+  const int grid = (int)std::min<int64_t>(ntiles, 2 * (int64_t)num_sms);
+  k_atomconv_fwd_tc<<<grid, 256, FwdTcSmem::bytes, st>>>(a, w);
+  B2M_CK(cudaGetLastError());
+  g_launch_count++;
+}
+
+}  // namespace b2m
