@@ -65,7 +65,7 @@ static Nccl g_nccl;
 // ------------------------------------------------------------------------------------------
 struct AtomLayerW {
   float *W1s_k, *W1e_k, *W1t_k, *b1, *W1s_raw, *W1e_raw, *W1t_raw, *M, *W2k, *W2raw, *b2, *Wout_k, *Wout_raw;
-  float *W2can, *Mcan;  // tcgen05 operands (canonical UMMA layout, tf32 hi/lo planes)
+  float *W2can, *Mcan, *W2Tcan;  // tcgen05 operands (canonical UMMA layout, tf32 hi/lo planes)
 };
 struct BondLayerW {
   float *W1a_k, *W1b_k, *W1c_k, *Wg_k, *b1, *W1a_raw, *W1b_raw, *W1c_raw, *Wg_raw, *W2k, *W2raw, *b2, *Wout_k, *Wout_raw;
@@ -100,7 +100,8 @@ struct b2m_engine {
   // graph + workspace
   Graph g;
   bool have_graph = false;
-  std::vector<DBuf<float>> x, h, ang, upd;
+  std::vector<DBuf<float>> x, h, ang, upd, uv;
+  bool want_grads = true;
   DBuf<float> Ap, Cp, Qp, Ha, Hb, Xc, agg, aggB, y1p, y1, y2p, y2, e_atom, site;
   DBuf<float> gx, gh, gang, gA, gC, gQ, gHa, gHb, gXc, gagg, gupd, gaggB, gd, gdb, gbvec, gy1, gy2;
   DBuf<float> forces, sendbuf, recvbuf, site_full;
@@ -263,6 +264,7 @@ static void finalize_weights(b2m_engine* e) {
       const std::vector<float> W2L(W2.begin(), W2.begin() + 4096), W2G(W2.begin() + 4096, W2.end());
       put(q + "W2can", vcat(canon_split(W2L, 64, 64, 64), canon_split(W2G, 64, 64, 64)));
       put(q + "Mcan", canon_split(M, 128, 9, 16));
+      put(q + "W2Tcan", vcat(canon_split(transpose(W2L, 64, 64), 64, 64, 64), canon_split(transpose(W2G, 64, 64), 64, 64, 64)));
     }
   }
   for (int l = 0; l < nb - 1; l++) {
@@ -347,7 +349,7 @@ static void finalize_weights(b2m_engine* e) {
     w.W1s_raw = dp(q + "W1s_raw"), w.W1e_raw = dp(q + "W1e_raw"), w.W1t_raw = dp(q + "W1t_raw");
     w.M = dp(q + "M"), w.W2k = dp(q + "W2k"), w.W2raw = dp(q + "W2raw"), w.b2 = dp(q + "b2");
     w.Wout_k = dp(q + "Wout_k"), w.Wout_raw = dp(q + "Wout_raw");
-    w.W2can = dp(q + "W2can"), w.Mcan = dp(q + "Mcan");
+    w.W2can = dp(q + "W2can"), w.Mcan = dp(q + "Mcan"), w.W2Tcan = dp(q + "W2Tcan");
   }
   e->bw.resize(nb - 1);
   for (int l = 0; l < nb - 1; l++) {
@@ -378,6 +380,9 @@ static void alloc_workspace(b2m_engine* e) {
   for (auto& b : e->h) b.ensure(bl * D + 64);
   for (auto& b : e->ang) b.ensure(A * D + 64);
   for (auto& b : e->upd) b.ensure(bo * D + 64);
+  e->uv.resize(nb);
+  if (e->use_tc)
+    for (auto& b : e->uv) b.ensure(E * D2 + 64);  // second-layer pre-activations kept for the backward
   e->Ap.ensure(nl * D2 + 64), e->Cp.ensure(no * D2 + 64), e->Qp.ensure(bo * D2 + 64);
   e->Ha.ensure(bl * D2 + 64), e->Hb.ensure(bo * D2 + 64), e->Xc.ensure(nl * D2 + 64);
   e->agg.ensure(no * D + 64), e->aggB.ensure(bo * D + 64);
@@ -481,7 +486,8 @@ static void atom_layer_fwd(b2m_engine* e, int l) {
   B2M_CK(cudaEventCreate(&e1));
   B2M_CK(cudaEventRecord(e0, e->st));
   if (e->use_tc) {
-    AtomConvTcW tw{w.W2can, w.Mcan};
+    AtomConvTcW tw{w.W2can, w.Mcan, w.W2Tcan};
+    a.uv_save = e->want_grads ? e->uv[l].p : nullptr;
     launch_atomconv_fwd_tc(e->st, a, tw, e->num_sms);
   } else {
     launch_atomconv_fwd(e->st, a);
@@ -505,7 +511,13 @@ static void atom_layer_bwd(b2m_engine* e, int l) {
     launch_zero_rows(e->st, e->gC.p, (int64_t)g.n_own * D2);
     a.gA = e->gA.p, a.gC = e->gC.p, a.gQ = e->gQ.p;
   }
-  launch_atomconv_bwd(e->st, a);
+  if (e->use_tc) {
+    AtomConvTcW tw{w.W2can, w.Mcan, w.W2Tcan};
+    a.uv = e->uv[l].p;
+    launch_atomconv_bwd_tc(e->st, a, tw, e->num_sms);
+  } else {
+    launch_atomconv_bwd(e->st, a);
+  }
   if (need_gx) {
     launch_gemm(e->st, e->gA.p, D2, w.W1s_raw, e->gx.p, D, g.n_loc, D, D2, nullptr, nullptr, 0, true);
     launch_gemm(e->st, e->gC.p, D2, w.W1t_raw, e->gx.p, D, g.n_own, D, D2, nullptr, nullptr, 0, true);
@@ -646,6 +658,7 @@ static void run(b2m_engine* e, bool grads) {
   e->gather_ev.clear();
   const long long l0 = g_launch_count;
   B2M_CK(cudaEventRecord(e->ev[0], e->st));
+  e->want_grads = grads;
   forward(e);
   B2M_CK(cudaEventRecord(e->ev[1], e->st));
   if (grads) backward(e);

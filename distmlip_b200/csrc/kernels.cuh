@@ -61,6 +61,9 @@ struct AtomConvArgs {
   float* gC;          // [n_own,128] (+=)
   float* gQ;          // [B_own,128] (=)
   float* gd;          // [E] (+=)
+  // tcgen05 path: second-layer pre-activations (u | v) saved by the forward for the backward
+  float* uv_save;       // [E,128] or nullptr (forward)
+  const float* uv;      // [E,128] (backward)
 };
 void launch_atomconv_fwd(cudaStream_t st, const AtomConvArgs& a);
 void launch_atomconv_bwd(cudaStream_t st, const AtomConvArgs& a);
@@ -134,8 +137,10 @@ void launch_scatter_add_rows(cudaStream_t st, int n, int width, const int* idx, 
 // ---------------------------------------------------------------------------------------------
 namespace b2m {
 struct AtomConvTcW {
-  const float* W2can;  // [4][4096]: W2L hi, W2L lo, W2G hi, W2G lo   (N=64, K=64)
-  const float* Mcan;   // [2][2048]: M hi, M lo                        (N=128, K=16; k>=9 zero)
+  const float* W2can;   // [4][4096]: W2L hi, W2L lo, W2G hi, W2G lo   (N=64, K=64)
+  const float* Mcan;    // [2][2048]: M hi, M lo                        (N=128, K=16; k>=9 zero)
+  const float* W2Tcan;  // [4][4096]: W2L^T hi, lo, W2G^T hi, lo        (backward: ghid = g . W2)
 };
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
+void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
 }  // namespace b2m

@@ -292,12 +292,26 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
 #pragma unroll
         for (int i = 0; i < 16; i++) {
           const int c = c0 + ch * 16 + i;
-          const float oL = silu_(__uint_as_float(u[i]) + b2s[c]);
-          const float oG = sigm_(__uint_as_float(g[i]) + b2s[64 + c]);
+          const float uu = __uint_as_float(u[i]) + b2s[c], vv = __uint_as_float(g[i]) + b2s[64 + c];
+          u[i] = __float_as_uint(uu);
+          g[i] = __float_as_uint(vv);
+          const float oL = silu_(uu);
+          const float oG = sigm_(vv);
           float wab = 0.f;
 #pragma unroll
           for (int k = 0; k < 9; k++) wab = fmaf(bek[k], wabW[c * 9 + k], wab);
           mv[ch * 16 + i] = valid ? oL * oG * wab : 0.f;
+        }
+        if (a.uv_save != nullptr && valid) {
+          float4* pu = reinterpret_cast<float4*>(a.uv_save + (size_t)(e0 + r) * D2 + c0 + ch * 16);
+          float4* pv = reinterpret_cast<float4*>(a.uv_save + (size_t)(e0 + r) * D2 + 64 + c0 + ch * 16);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            pu[i] = make_float4(__uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]), __uint_as_float(u[4 * i + 2]),
+                                __uint_as_float(u[4 * i + 3]));
+            pv[i] = make_float4(__uint_as_float(g[4 * i]), __uint_as_float(g[4 * i + 1]), __uint_as_float(g[4 * i + 2]),
+                                __uint_as_float(g[4 * i + 3]));
+          }
         }
       }
     }
@@ -332,6 +346,342 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
+}
+
+// ============================================================================================
+// atom conv backward on tcgen05
+//   recomputes only the first-layer pre-activation (M.be on the tensor core + gathers); second-layer
+//   pre-activations (u,v) come from the forward; ghid = [gu . W2L | gv . W2G] on the tensor core;
+//   gpre = ghid * silu'(pre) is scattered: segmented sums -> gC[dst], RED -> gA[src], store -> gQ[bond],
+//   and contracted with M and dbe/dd for dE/dd_e.
+// ============================================================================================
+__device__ __forceinline__ void rbf_env_both(float d, float freq, const RadialParams& rp, float& be, float& dbe) {
+  const float invd = 1.f / d;
+  const float wq = freq / rp.rc;
+  float s, c;
+  sincosf(d * wq, &s, &c);
+  const float rbf = rp.norm * s * invd;
+  const float drbf = rp.norm * (wq * c * invd - s * invd * invd);
+  const int p = rp.p;
+  const float c1 = -(p + 1) * (p + 2) * 0.5f, c2 = (float)(p * (p + 2)), c3 = -p * (p + 1) * 0.5f;
+  const float rho = rbf / rp.rc;
+  const float rm1 = ipow_(rho, p - 1);
+  const float r0 = rm1 * rho, r1 = r0 * rho, r2 = r1 * rho;
+  const float env = 1.f + c1 * r0 + c2 * r1 + c3 * r2;
+  const float denv = (c1 * p * rm1 + c2 * (p + 1) * r0 + c3 * (p + 2) * r1) / rp.rc;
+  const bool ok = rbf <= rp.rc;
+  be = ok ? env * rbf : 0.f;
+  dbe = ok ? (env + rbf * denv) * drbf : 0.f;
+}
+
+struct BwdTcSmem {
+  static constexpr int kBar = 0;
+  static constexpr int kW2T = 64;                  // 4 x 4096
+  static constexpr int kM = kW2T + 4 * 4096;       // 2 x 2048 (canonical)
+  static constexpr int kStage = kM + 2 * 2048;     // [64][65]
+  static constexpr int kBe = kStage + 64 * 65;     // [128][9]
+  static constexpr int kDbe = kBe + 128 * 9;       // [128][9]
+  static constexpr int kWab = kDbe + 128 * 9;      // 576
+  static constexpr int kD = kWab + 576;            // [128]
+  static constexpr int kIdx = kD + 128;            // 3 x 128 ints
+  static constexpr int kTotal = kIdx + 3 * 128;
+  static constexpr size_t bytes = (size_t)kTotal * 4;
+};
+
+__global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a, const AtomConvTcW w) {
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + BwdTcSmem::kBar);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + BwdTcSmem::kBar + 16);
+  float* W2Ts = smem + BwdTcSmem::kW2T;
+  float* Ms = smem + BwdTcSmem::kM;
+  float* stage = smem + BwdTcSmem::kStage;
+  float* be_s = smem + BwdTcSmem::kBe;
+  float* dbe_s = smem + BwdTcSmem::kDbe;
+  float* wabW = smem + BwdTcSmem::kWab;
+  float* s_d = smem + BwdTcSmem::kD;
+  int* s_src = reinterpret_cast<int*>(smem + BwdTcSmem::kIdx);
+  int* s_dst = s_src + 128;
+  int* s_bond = s_dst + 128;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int r = q * 32 + lane;
+  const int c0 = half * 32;
+  const bool useQ = a.Qproj != nullptr;
+  const bool need_gx = a.gA != nullptr;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init_(&mbar[0], 1);
+    mbar_init_(&mbar[1], 1);
+    mbar_init_(&mbar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 4 * 1024; i += 256) reinterpret_cast<float4*>(W2Ts)[i] = reinterpret_cast<const float4*>(w.W2Tcan)[i];
+  for (int i = tid; i < 2 * 512; i += 256) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
+  for (int i = tid; i < 576; i += 256) wabW[i] = a.Wabw[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tptr;
+  const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+  constexpr uint32_t COL_H = 0, COL_D = 128;
+  const uint32_t w2t_addr = s_u32(W2Ts), m_addr = s_u32(Ms);
+  uint32_t phase = 0;
+
+  const int64_t ntiles = (a.E + 127) / 128;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t e0 = t * 128;
+    const int nvalid = (int)min((int64_t)128, a.E - e0);
+    if (tid < 128) {
+      int src = 0, dst = -1, bond = -1;
+      float d = 1.f;
+      if (tid < nvalid) {
+        const int64_t e = e0 + tid;
+        src = a.e_src[e];
+        dst = a.e_dst[e];
+        bond = a.e_bond[e];
+        d = a.e_vec[e].w;
+      }
+      s_src[tid] = src;
+      s_dst[tid] = dst;
+      s_bond[tid] = bond;
+      s_d[tid] = d;
+    }
+    __syncthreads();
+    {
+      const float d = s_d[r];
+      const int k0 = half ? 5 : 0, k1 = half ? 9 : 5;
+      for (int k = k0; k < k1; k++) {
+        float be = 0.f, dbe = 0.f;
+        if (r < nvalid) rbf_env_both(d, a.rp.freq[k], a.rp, be, dbe);
+        be_s[r * 9 + k] = be;
+        dbe_s[r * 9 + k] = dbe;
+      }
+    }
+    __syncthreads();
+    float bek[9], dbek[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      bek[k] = be_s[r * 9 + k];
+      dbek[k] = dbe_s[r * 9 + k];
+    }
+    if (half == 0) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const float x = k < 9 ? bek[k] : 0.f;
+        const uint32_t h = tf32_hi_bits(x);
+        hi[k] = h;
+        lo[k] = __float_as_uint(x - __uint_as_float(h));
+      }
+      tmem_st16(tlane + COL_H, hi);
+      tmem_st16(tlane + COL_H + 16, lo);
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      uint32_t acc = 0;
+#pragma unroll
+      for (int term = 0; term < 3; term++) {
+        const uint32_t acol = term == 1 ? 16u : 0u;
+        const uint32_t bsel = m_addr + (term == 2 ? 2048u * 4u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+          umma_ts(tbase + COL_D, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 4096u, 2048u, 128u), kIdescN128, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(&mbar[0]);
+    }
+    const int src = s_src[r], dst = s_dst[r], bond = s_bond[r];
+    const bool valid = r < nvalid;
+    const bool viaQ = useQ && bond >= 0;
+    const float* Arow = a.Aproj + (size_t)src * D2;
+    const float* Crow = a.Cproj + (size_t)(valid ? dst : 0) * D2;
+    const float* Qrow = viaQ ? a.Qproj + (size_t)bond * D2 : nullptr;
+    const float* uvrow = a.uv + (size_t)(valid ? e0 + r : 0) * D2;
+    const float* gmrow = a.gagg + (size_t)(valid ? dst : 0) * D;
+    float gdpart = 0.f;   // dE/dd_e contribution of this thread's columns
+    float gbeM[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) gbeM[k] = 0.f;
+
+#pragma unroll 1
+    for (int br = 0; br < 2; br++) {
+      mbar_wait_(&mbar[br], phase);
+      tc_fence_after();
+      const int cb = br * 64 + c0;
+      float ds[32];  // silu'(pre) for my 32 columns of this branch
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t v[16], hi[16], lo[16];
+        tmem_ld16(tlane + COL_D + cb + ch * 16, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float4 x = *reinterpret_cast<const float4*>(Arow + cb + ch * 16 + i * 4);
+          const float4 y = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
+          float4 t4 = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                  __uint_as_float(v[4 * i + 3]));
+          if (viaQ) t4 = *reinterpret_cast<const float4*>(Qrow + cb + ch * 16 + i * 4);
+          const float p0 = t4.x + x.x + y.x, p1 = t4.y + x.y + y.y, p2 = t4.z + x.z + y.z, p3 = t4.w + x.w + y.w;
+          float sg;
+          sg = sigm_(p0), ds[ch * 16 + 4 * i] = sg * (1.f + p0 * (1.f - sg));
+          sg = sigm_(p1), ds[ch * 16 + 4 * i + 1] = sg * (1.f + p1 * (1.f - sg));
+          sg = sigm_(p2), ds[ch * 16 + 4 * i + 2] = sg * (1.f + p2 * (1.f - sg));
+          sg = sigm_(p3), ds[ch * 16 + 4 * i + 3] = sg * (1.f + p3 * (1.f - sg));
+        }
+        // gradient w.r.t. this branch's second-layer pre-activation (gu for br=0, gv for br=1)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int c = c0 + ch * 16 + i * 4;
+          const float4 u4 = *reinterpret_cast<const float4*>(uvrow + c);
+          const float4 v4 = *reinterpret_cast<const float4*>(uvrow + 64 + c);
+          const float4 g4 = *reinterpret_cast<const float4*>(gmrow + c);
+          const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            float wab = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; k++) wab = fmaf(bek[k], wabW[(c + j) * 9 + k], wab);
+            const float su = sigm_(uu[j]), oG = sigm_(vv[j]);
+            const float oL = uu[j] * su;
+            float g;
+            if (br == 0) {
+              g = gg[j] * oG * wab * (su * (1.f + uu[j] * (1.f - su)));
+              // d/d w_ab -> d/d d_e through d(be)/dd (only once per column: do it in the br == 0 pass)
+              float wabp = 0.f;
+#pragma unroll
+              for (int k = 0; k < 9; k++) wabp = fmaf(dbek[k], wabW[(c + j) * 9 + k], wabp);
+              gdpart = fmaf(gg[j] * oL * oG, wabp, gdpart);
+            } else {
+              g = gg[j] * oL * wab * oG * (1.f - oG);
+            }
+            if (!valid) g = 0.f;
+            const uint32_t h = tf32_hi_bits(g);
+            hi[4 * i + j] = h;
+            lo[4 * i + j] = __float_as_uint(g - __uint_as_float(h));
+          }
+        }
+        tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
+        tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {  // ghid[:, br*64 .. +64] = g[128 x 64] . W2 (B operand = W2^T, canonical)
+        tc_fence_after();
+        uint32_t acc = 0;
+#pragma unroll
+        for (int term = 0; term < 3; term++) {
+          const uint32_t acol = term == 1 ? 64u : 0u;
+          const uint32_t bsel = w2t_addr + (uint32_t)(br * 2 + (term == 2 ? 1 : 0)) * 4096u * 4u;
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) {
+            umma_ts(tbase + COL_D + br * 64, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 2048u, 1024u, 128u),
+                    kIdescN64, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&mbar[br + 1]);
+      }
+      // the next branch's first-layer columns live in the other half of D: wait for this GEMM before
+      // touching H again; meanwhile nothing else to do for this tile.
+      mbar_wait_(&mbar[br + 1], phase);
+      tc_fence_after();
+      // gpre = ghid * silu'(pre)
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t v[16];
+        tmem_ld16(tlane + COL_D + br * 64 + c0 + ch * 16, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; i++) ds[ch * 16 + i] *= __uint_as_float(v[i]);
+      }
+      // dE/d be through the radial first-layer term (not for bond rows fed by Q)
+      if (!viaQ) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float* Mj = a.M + (size_t)(cb + i) * 9;
+#pragma unroll
+          for (int k = 0; k < 9; k++) gbeM[k] = fmaf(ds[i], __ldg(Mj + k), gbeM[k]);
+        }
+      }
+      if (need_gx) {
+#pragma unroll 1
+        for (int hp = 0; hp < 2; hp++) {
+          if ((q >> 1) == hp) {
+            const int rr = r - hp * 64;
+#pragma unroll
+            for (int i = 0; i < 32; i++) stage[rr * 65 + c0 + i] = ds[i];
+          }
+          __syncthreads();
+          {
+            const int c = tid & 63, part = tid >> 6;
+            const int col = br * 64 + c;
+            float sum = 0.f;
+            int cur = -1;
+            const int rbeg = part * 16;
+            for (int rr = rbeg; rr < rbeg + 16; rr++) {
+              const int row = hp * 64 + rr;
+              const int k = s_dst[row];
+              const float val = stage[rr * 65 + c];
+              if (k != cur) {
+                if (cur >= 0) atomicAdd(&a.gC[(size_t)cur * D2 + col], sum);
+                cur = k;
+                sum = 0.f;
+              }
+              if (k >= 0) {
+                sum += val;
+                atomicAdd(&a.gA[(size_t)s_src[row] * D2 + col], val);
+                const int bnd = s_bond[row];
+                if (useQ && bnd >= 0) a.gQ[(size_t)bnd * D2 + col] = val;
+              }
+            }
+            if (cur >= 0) atomicAdd(&a.gC[(size_t)cur * D2 + col], sum);
+          }
+          __syncthreads();
+        }
+      }
+      // mbar indices: br=0 used mbar[0] (GEMM1) and mbar[1]; br=1 must wait on "GEMM of branch 0 done",
+      // which it already has (above); re-arm by pointing the loop's first wait at an already-passed barrier.
+    }
+    phase ^= 1;
+    {
+      float s = gdpart;
+#pragma unroll
+      for (int k = 0; k < 9; k++) s = fmaf(gbeM[k], dbek[k], s);
+      stage[tid] = valid ? s : 0.f;
+      tc_fence_before();
+      __syncthreads();
+      if (tid < nvalid) a.gd[e0 + tid] += stage[tid] + stage[128 + tid];
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
+}
+
+void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
+  if (a.E <= 0) return;
+  static bool attr = false;
+  if (!attr) {
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
+    attr = true;
+  }
+  const int64_t ntiles = (a.E + 127) / 128;
+  const int grid = (int)std::min<int64_t>(ntiles, 2 * (int64_t)num_sms);
+  k_atomconv_bwd_tc<<<grid, 256, BwdTcSmem::bytes, st>>>(a, w);
+  B2M_CK(cudaGetLastError());
+  g_launch_count++;
 }
 
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
