@@ -70,6 +70,7 @@ struct AtomLayerW {
 struct BondLayerW {
   float *W1a_k, *W1b_k, *W1c_k, *Wg_k, *b1, *W1a_raw, *W1b_raw, *W1c_raw, *Wg_raw, *W2k, *W2raw, *b2, *Wout_k, *Wout_raw;
   float *WAa_k, *WAb_k, *WAc_k, *WAg_k, *bA, *WAa_raw, *WAb_raw, *WAc_raw, *WAg_raw;
+  float *Wgcan, *W2can, *W2Tcan, *WgTcan, *WAgcan, *WAgTcan;  // tcgen05 operands
 };
 
 }  // namespace b2m
@@ -100,7 +101,7 @@ struct b2m_engine {
   // graph + workspace
   Graph g;
   bool have_graph = false;
-  std::vector<DBuf<float>> x, h, ang, upd, uv;
+  std::vector<DBuf<float>> x, h, ang, upd, uv, uvB, dsB, uvA;
   bool want_grads = true;
   DBuf<float> Ap, Cp, Qp, Ha, Hb, Xc, agg, aggB, y1p, y1, y2p, y2, e_atom, site;
   DBuf<float> gx, gh, gang, gA, gC, gQ, gHa, gHb, gXc, gagg, gupd, gaggB, gd, gdb, gbvec, gy1, gy2;
@@ -310,6 +311,20 @@ static void finalize_weights(b2m_engine* e) {
     put(q + "WAb_raw", WAb);
     put(q + "WAc_raw", WAc);
     put(q + "WAg_raw", WAg);
+    {
+      auto rows64 = [](const std::vector<float>& m, int br) {
+        return std::vector<float>(m.begin() + (size_t)br * 4096, m.begin() + (size_t)(br + 1) * 4096);
+      };
+      const std::vector<float> W2L(W2.begin(), W2.begin() + 4096), W2G(W2.begin() + 4096, W2.end());
+      put(q + "Wgcan", canon_split(W1g, 128, 64, 64));
+      put(q + "W2can", vcat(canon_split(W2L, 64, 64, 64), canon_split(W2G, 64, 64, 64)));
+      put(q + "W2Tcan", vcat(canon_split(transpose(W2L, 64, 64), 64, 64, 64), canon_split(transpose(W2G, 64, 64), 64, 64, 64)));
+      put(q + "WgTcan", vcat(canon_split(transpose(rows64(W1g, 0), 64, 64), 64, 64, 64),
+                             canon_split(transpose(rows64(W1g, 1), 64, 64), 64, 64, 64)));
+      put(q + "WAgcan", canon_split(WAg, 128, 64, 64));
+      put(q + "WAgTcan", vcat(canon_split(transpose(rows64(WAg, 0), 64, 64), 64, 64, 64),
+                              canon_split(transpose(rows64(WAg, 1), 64, 64), 64, 64, 64)));
+    }
   }
   const auto& F0 = W(e, "final_layer.layers.0.weight", {D, D});
   const auto& F1 = W(e, "final_layer.layers.1.weight", {D, D});
@@ -362,6 +377,8 @@ static void finalize_weights(b2m_engine* e) {
     w.WAa_k = dp(q + "WAa_k"), w.WAb_k = dp(q + "WAb_k"), w.WAc_k = dp(q + "WAc_k"), w.WAg_k = dp(q + "WAg_k");
     w.bA = dp(q + "bA"), w.WAa_raw = dp(q + "WAa_raw"), w.WAb_raw = dp(q + "WAb_raw"), w.WAc_raw = dp(q + "WAc_raw");
     w.WAg_raw = dp(q + "WAg_raw");
+    w.Wgcan = dp(q + "Wgcan"), w.W2can = dp(q + "W2can"), w.W2Tcan = dp(q + "W2Tcan"), w.WgTcan = dp(q + "WgTcan");
+    w.WAgcan = dp(q + "WAgcan"), w.WAgTcan = dp(q + "WAgTcan");
   }
   e->finalized = true;
 }
@@ -383,6 +400,12 @@ static void alloc_workspace(b2m_engine* e) {
   e->uv.resize(nb);
   if (e->use_tc)
     for (auto& b : e->uv) b.ensure(E * D2 + 64);  // second-layer pre-activations kept for the backward
+  e->uvB.resize(nb - 1), e->dsB.resize(nb - 1), e->uvA.resize(nb - 1);
+  if (e->use_tc) {
+    for (auto& b : e->uvB) b.ensure(A * D2 + 64);
+    for (auto& b : e->dsB) b.ensure(A * D2 + 64);
+    for (int l = 0; l < nb - 2; l++) e->uvA[l].ensure(A * D2 + 64);
+  }
   e->Ap.ensure(nl * D2 + 64), e->Cp.ensure(no * D2 + 64), e->Qp.ensure(bo * D2 + 64);
   e->Ha.ensure(bl * D2 + 64), e->Hb.ensure(bo * D2 + 64), e->Xc.ensure(nl * D2 + 64);
   e->agg.ensure(no * D + 64), e->aggB.ensure(bo * D + 64);
@@ -539,7 +562,28 @@ static LineArgs line_args(b2m_engine* e, int l, bool hidden) {
   } else {
     a.Wgk = w.WAg_k, a.Wgraw = w.WAg_raw;
   }
+  if (e->use_tc) {
+    float* uvp = hidden ? e->uvB[l].p : e->uvA[l].p;
+    a.uv = uvp, a.ds = hidden ? e->dsB[l].p : nullptr;
+    if (e->want_grads) a.uv_save = uvp, a.ds_save = hidden ? e->dsB[l].p : nullptr;
+  }
   return a;
+}
+static LineTcW line_tcw(b2m_engine* e, int l, bool hidden) {
+  const BondLayerW& w = e->bw[l];
+  LineTcW t;
+  if (hidden) {
+    t.Wgcan = w.Wgcan, t.W2can = w.W2can, t.W2Tcan = w.W2Tcan, t.WgTcan = w.WgTcan;
+  } else {
+    t.Wgcan = w.WAgcan, t.W2can = nullptr, t.W2Tcan = nullptr, t.WgTcan = w.WAgTcan;
+  }
+  return t;
+}
+static void line_fwd_dispatch(b2m_engine* e, int l, bool hidden, const LineArgs& a) {
+  if (e->use_tc)
+    launch_line_fwd_tc(e->st, a, line_tcw(e, l, hidden), hidden, e->num_sms);
+  else
+    launch_line_fwd(e->st, a, hidden);
 }
 static void line_projections(b2m_engine* e, int l, bool hidden) {
   Graph& g = e->g;
@@ -558,7 +602,10 @@ static void line_bwd_common(b2m_engine* e, int l, bool hidden, LineArgs& a) {
   launch_zero_rows(e->st, e->gHb.p, (int64_t)g.B_own * D2);
   launch_zero_rows(e->st, e->gXc.p, (int64_t)g.n_loc * D2);
   a.gang = e->gang.p, a.gHa = e->gHa.p, a.gHb = e->gHb.p, a.gXc = e->gXc.p;
-  launch_line_bwd(e->st, a, hidden);
+  if (e->use_tc)
+    launch_line_bwd_tc(e->st, a, line_tcw(e, l, hidden), hidden, e->num_sms);
+  else
+    launch_line_bwd(e->st, a, hidden);
   launch_gemm(e->st, e->gHa.p, D2, hidden ? w.W1a_raw : w.WAa_raw, e->gh.p, D, g.B_loc, D, D2, nullptr, nullptr, 0, true);
   launch_gemm(e->st, e->gHb.p, D2, hidden ? w.W1b_raw : w.WAb_raw, e->gh.p, D, g.B_own, D, D2, nullptr, nullptr, 0, true);
   launch_gemm(e->st, e->gXc.p, D2, hidden ? w.W1c_raw : w.WAc_raw, e->gx.p, D, g.n_loc, D, D2, nullptr, nullptr, 0, true);
@@ -578,7 +625,7 @@ static void forward(b2m_engine* e) {
     launch_zero_rows(e->st, e->aggB.p, (int64_t)g.B_own * D);
     LineArgs a = line_args(e, l, true);
     a.aggB = e->aggB.p;
-    launch_line_fwd(e->st, a, true);
+    line_fwd_dispatch(e, l, true, a);
     launch_gemm(e->st, e->aggB.p, D, w.Wout_k, e->upd[l].p, D, g.B_own, D, D, nullptr, nullptr, 0, false);
     launch_bond_update_fwd(e->st, g.B_own, g.b_vec.p, e->rp3, e->d_W3bw, e->h[l].p, e->upd[l].p, e->h[l + 1].p);
     if (l < nb - 2) {
@@ -588,7 +635,7 @@ static void forward(b2m_engine* e) {
       line_projections(e, l, false);
       LineArgs b = line_args(e, l, false);
       b.ang_out = e->ang[l + 1].p;
-      launch_line_fwd(e->st, b, false);
+      line_fwd_dispatch(e, l, false, b);
     }
   }
   // site-wise readout after block n-2 (chgnet.py:392-398)

@@ -92,6 +92,11 @@ struct LineArgs {
   float* gHa;          // [B_loc,128] (+=)
   float* gHb;          // [B_own,128] (+=)
   float* gXc;          // [n_loc,128] (+=)
+  // tcgen05 path: tensors saved by the forward for the backward
+  float* uv_save;       // [A,128] last-layer pre-activations (u | v)
+  float* ds_save;       // [A,128] silu'(first-layer pre-activation)   (HIDDEN only)
+  const float* uv;
+  const float* ds;
 };
 void launch_line_fwd(cudaStream_t st, const LineArgs& a, bool hidden);
 void launch_line_bwd(cudaStream_t st, const LineArgs& a, bool hidden);
@@ -143,4 +148,12 @@ struct AtomConvTcW {
 };
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
+struct LineTcW {
+  const float* Wgcan;   // [2][8192]: first-layer angle block (N=128, K=64) hi, lo
+  const float* W2can;   // [4][4096]: second layers (HIDDEN)
+  const float* W2Tcan;  // [4][4096]: transposed second layers (HIDDEN, backward)
+  const float* WgTcan;  // [4][4096]: per branch (N=64 angle cols, K=64 first-layer cols): L hi, L lo, G hi, G lo
+};
+void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms);
+void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms);
 }  // namespace b2m

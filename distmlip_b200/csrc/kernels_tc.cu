@@ -699,3 +699,556 @@ void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
 }
 
 }  // namespace b2m
+
+// ============================================================================================
+// line-graph kernels on tcgen05: bond conv (HIDDEN) and angle update (!HIDDEN)
+//   one CTA per SM, 512 threads = two independent 256-thread row groups (each: one 128-angle tile in
+//   flight, 256 TMEM columns, its own named barrier) sharing one copy of the weights in shared memory.
+// ============================================================================================
+namespace b2m {
+
+__device__ __forceinline__ void gbar(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
+
+struct LineTcSmem {
+  static constexpr int kBar = 0;                    // 2 groups x 6 mbarriers, tmem ptr   (64 floats)
+  static constexpr int kWA = 64;                    // 16384 floats: fwd: Wg can   | bwd: WgT can (4 x 4096)
+  static constexpr int kWB = kWA + 16384;           // 16384 floats: fwd: W2 can   | bwd: W2T can
+  static constexpr int kB2 = kWB + 16384;           // 128
+  static constexpr int kGrp = kB2 + 128;            // per group: stage [64][65] + 3 x 128 ints
+  static constexpr int kGrpSize = 64 * 65 + 3 * 128;
+  static constexpr int kTotal = kGrp + 2 * kGrpSize;
+  static constexpr size_t bytes = (size_t)kTotal * 4;
+};
+
+template <bool HIDDEN>
+__global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const LineTcW w) {
+  extern __shared__ __align__(1024) float smem[];
+  const int tid = threadIdx.x;
+  const int g = tid >> 8, gt = tid & 255;
+  const int warp = gt >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int r = q * 32 + lane, c0 = half * 32;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + LineTcSmem::kBar) + g * 6;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + LineTcSmem::kBar + 48);
+  float* WAs = smem + LineTcSmem::kWA;
+  float* WBs = smem + LineTcSmem::kWB;
+  float* b2s = smem + LineTcSmem::kB2;
+  float* stage = smem + LineTcSmem::kGrp + g * LineTcSmem::kGrpSize;
+  int* s_a = reinterpret_cast<int*>(stage + 64 * 65);
+  int* s_b = s_a + 128;
+  int* s_c = s_b + 128;
+
+  if ((tid >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (gt == 0) {
+    for (int i = 0; i < 6; i++) mbar_init_(&mbar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 4096; i += 512) reinterpret_cast<float4*>(WAs)[i] = reinterpret_cast<const float4*>(w.Wgcan)[i];
+  if (HIDDEN)
+    for (int i = tid; i < 4096; i += 512) reinterpret_cast<float4*>(WBs)[i] = reinterpret_cast<const float4*>(w.W2can)[i];
+  if (tid < 128) b2s[tid] = (HIDDEN && a.b2) ? a.b2[tid] : 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tptr + (uint32_t)g * 256u;
+  const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+  constexpr uint32_t COL_H = 0, COL_D = 128;
+  const uint32_t wa_addr = s_u32(WAs), wb_addr = s_u32(WBs);
+  uint32_t phase = 0;
+
+  const int64_t ntiles = (a.A + 127) / 128;
+  for (int64_t t = 2 * (int64_t)blockIdx.x + g; t < ntiles; t += 2 * (int64_t)gridDim.x) {
+    const int64_t r0 = t * 128;
+    const int nvalid = (int)min((int64_t)128, a.A - r0);
+    if (gt < 128) {
+      int ia = 0, ib = -1, ic = 0;
+      if (gt < nvalid) {
+        ia = a.a_in[r0 + gt];
+        ib = a.a_out[r0 + gt];
+        ic = a.a_ctr[r0 + gt];
+      }
+      s_a[gt] = ia;
+      s_b[gt] = ib;
+      s_c[gt] = ic;
+    }
+    gbar(g);
+    const bool valid = r < nvalid;
+    const int ia = s_a[r], ib = s_b[r], ic = s_c[r];
+    const float* angrow = a.ang + (size_t)(valid ? r0 + r : 0) * D;
+    float angv[32];
+    {  // my half of the angle row -> TMEM operand (hi | lo)
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          float4 x = *reinterpret_cast<const float4*>(angrow + c0 + ch * 16 + i * 4);
+          if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            angv[ch * 16 + 4 * i + j] = xv[j];
+            const uint32_t h = tf32_hi_bits(xv[j]);
+            hi[4 * i + j] = h;
+            lo[4 * i + j] = __float_as_uint(xv[j] - __uint_as_float(h));
+          }
+        }
+        tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
+        tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
+      }
+    }
+    tc_wait_st();
+    tc_fence_before();
+    gbar(g);
+    if (gt == 0) {  // GEMM1: D[128 x 128] = ang[128 x 64] . Wg^T
+      tc_fence_after();
+      uint32_t acc = 0;
+#pragma unroll
+      for (int term = 0; term < 3; term++) {
+        const uint32_t acol = term == 1 ? 64u : 0u;
+        const uint32_t bsel = wa_addr + (term == 2 ? 8192u * 4u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+          umma_ts(tbase + COL_D, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 4096u, 2048u, 128u), kIdescN128, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(&mbar[0]);
+    }
+    const float* Harow = a.Ha + (size_t)ia * D2;
+    const float* Hbrow = a.Hb + (size_t)(valid ? ib : 0) * D2;
+    const float* Xcrow = a.Xc + (size_t)ic * D2;
+    if (HIDDEN) {
+#pragma unroll 1
+      for (int br = 0; br < 2; br++) {
+        mbar_wait_(&mbar[br], phase);
+        tc_fence_after();
+        const int cb = br * 64 + c0;
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          uint32_t v[16], hi[16], lo[16];
+          tmem_ld16(tlane + COL_D + cb + ch * 16, v);
+          tc_wait_ld();
+          float dsv[16];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float4 x = *reinterpret_cast<const float4*>(Harow + cb + ch * 16 + i * 4);
+            const float4 y = *reinterpret_cast<const float4*>(Hbrow + cb + ch * 16 + i * 4);
+            const float4 z = *reinterpret_cast<const float4*>(Xcrow + cb + ch * 16 + i * 4);
+            const float p4[4] = {__uint_as_float(v[4 * i]) + x.x + y.x + z.x, __uint_as_float(v[4 * i + 1]) + x.y + y.y + z.y,
+                                 __uint_as_float(v[4 * i + 2]) + x.z + y.z + z.z,
+                                 __uint_as_float(v[4 * i + 3]) + x.w + y.w + z.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float sg = sigm_(p4[j]);
+              const float hval = valid ? p4[j] * sg : 0.f;
+              dsv[4 * i + j] = sg * (1.f + p4[j] * (1.f - sg));
+              const uint32_t h = tf32_hi_bits(hval);
+              hi[4 * i + j] = h;
+              lo[4 * i + j] = __float_as_uint(hval - __uint_as_float(h));
+            }
+          }
+          if (a.ds_save != nullptr && valid) {
+            float4* pd = reinterpret_cast<float4*>(a.ds_save + (size_t)(r0 + r) * D2 + cb + ch * 16);
+#pragma unroll
+            for (int i = 0; i < 4; i++) pd[i] = make_float4(dsv[4 * i], dsv[4 * i + 1], dsv[4 * i + 2], dsv[4 * i + 3]);
+          }
+          tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
+          tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        gbar(g);
+        if (gt == 0) {
+          tc_fence_after();
+          uint32_t acc = 0;
+#pragma unroll
+          for (int term = 0; term < 3; term++) {
+            const uint32_t acol = term == 1 ? 64u : 0u;
+            const uint32_t bsel = wb_addr + (uint32_t)(br * 2 + (term == 2 ? 1 : 0)) * 4096u * 4u;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+              umma_ts(tbase + COL_D + br * 64, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 2048u, 1024u, 128u),
+                      kIdescN64, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(&mbar[br + 1]);
+        }
+      }
+      mbar_wait_(&mbar[2], phase);
+      tc_fence_after();
+    } else {
+      mbar_wait_(&mbar[0], phase);
+      tc_fence_after();
+    }
+    // ---- last-layer pre-activations (u | v): HIDDEN from GEMM2 (+bias), else first layer + gathers ----
+    float mv[32];
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+      uint32_t u[16], v[16];
+      tmem_ld16(tlane + COL_D + c0 + ch * 16, u);
+      tmem_ld16(tlane + COL_D + 64 + c0 + ch * 16, v);
+      tc_wait_ld();
+      float uf[16], vf[16];
+      if (HIDDEN) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          uf[i] = __uint_as_float(u[i]) + b2s[c0 + ch * 16 + i];
+          vf[i] = __uint_as_float(v[i]) + b2s[64 + c0 + ch * 16 + i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int cL = c0 + ch * 16 + i * 4, cG = 64 + cL;
+          const float4 x = *reinterpret_cast<const float4*>(Harow + cL);
+          const float4 y = *reinterpret_cast<const float4*>(Hbrow + cL);
+          const float4 z = *reinterpret_cast<const float4*>(Xcrow + cL);
+          const float4 x2 = *reinterpret_cast<const float4*>(Harow + cG);
+          const float4 y2 = *reinterpret_cast<const float4*>(Hbrow + cG);
+          const float4 z2 = *reinterpret_cast<const float4*>(Xcrow + cG);
+          uf[4 * i] = __uint_as_float(u[4 * i]) + x.x + y.x + z.x;
+          uf[4 * i + 1] = __uint_as_float(u[4 * i + 1]) + x.y + y.y + z.y;
+          uf[4 * i + 2] = __uint_as_float(u[4 * i + 2]) + x.z + y.z + z.z;
+          uf[4 * i + 3] = __uint_as_float(u[4 * i + 3]) + x.w + y.w + z.w;
+          vf[4 * i] = __uint_as_float(v[4 * i]) + x2.x + y2.x + z2.x;
+          vf[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + x2.y + y2.y + z2.y;
+          vf[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + x2.z + y2.z + z2.z;
+          vf[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + x2.w + y2.w + z2.w;
+        }
+      }
+      if (a.uv_save != nullptr && valid) {
+        float4* pu = reinterpret_cast<float4*>(a.uv_save + (size_t)(r0 + r) * D2 + c0 + ch * 16);
+        float4* pv = reinterpret_cast<float4*>(a.uv_save + (size_t)(r0 + r) * D2 + 64 + c0 + ch * 16);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          pu[i] = make_float4(uf[4 * i], uf[4 * i + 1], uf[4 * i + 2], uf[4 * i + 3]);
+          pv[i] = make_float4(vf[4 * i], vf[4 * i + 1], vf[4 * i + 2], vf[4 * i + 3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i++) mv[ch * 16 + i] = valid ? silu_(uf[i]) * sigm_(vf[i]) : 0.f;
+    }
+    phase ^= 1;
+    tc_fence_before();
+    if (HIDDEN) {
+#pragma unroll 1
+      for (int hp = 0; hp < 2; hp++) {
+        if ((q >> 1) == hp) {
+          const int rr = r - hp * 64;
+#pragma unroll
+          for (int i = 0; i < 32; i++) stage[rr * 65 + c0 + i] = mv[i];
+        }
+        gbar(g);
+        {
+          const int c = gt & 63, part = gt >> 6;
+          float sum = 0.f;
+          int cur = -1;
+          const int rbeg = part * 16;
+          for (int rr = rbeg; rr < rbeg + 16; rr++) {
+            const int k = s_b[hp * 64 + rr];
+            if (k != cur) {
+              if (cur >= 0) atomicAdd(&a.aggB[(size_t)cur * D + c], sum);
+              cur = k;
+              sum = 0.f;
+            }
+            if (k >= 0) sum += stage[rr * 65 + c];
+          }
+          if (cur >= 0) atomicAdd(&a.aggB[(size_t)cur * D + c], sum);
+        }
+        gbar(g);
+      }
+    } else {
+      if (valid) {
+        float4* po = reinterpret_cast<float4*>(a.ang_out + (size_t)(r0 + r) * D + c0);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          po[i] = make_float4(angv[4 * i] + mv[4 * i], angv[4 * i + 1] + mv[4 * i + 1], angv[4 * i + 2] + mv[4 * i + 2],
+                              angv[4 * i + 3] + mv[4 * i + 3]);
+      }
+      gbar(g);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if ((tid >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tptr), "r"(512u));
+}
+
+// backward: gm -> g (per branch) -> [HIDDEN: ghid = g . W2 ; gpre = ghid * ds] -> scatter gpre, gang += gpre . Wg
+template <bool HIDDEN>
+__global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const LineTcW w) {
+  extern __shared__ __align__(1024) float smem[];
+  const int tid = threadIdx.x;
+  const int g = tid >> 8, gt = tid & 255;
+  const int warp = gt >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int r = q * 32 + lane, c0 = half * 32;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + LineTcSmem::kBar) + g * 6;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + LineTcSmem::kBar + 48);
+  float* WAs = smem + LineTcSmem::kWA;  // WgT can
+  float* WBs = smem + LineTcSmem::kWB;  // W2T can
+  float* stage = smem + LineTcSmem::kGrp + g * LineTcSmem::kGrpSize;
+  int* s_a = reinterpret_cast<int*>(stage + 64 * 65);
+  int* s_b = s_a + 128;
+  int* s_c = s_b + 128;
+
+  if ((tid >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (gt == 0) {
+    for (int i = 0; i < 6; i++) mbar_init_(&mbar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 4096; i += 512) reinterpret_cast<float4*>(WAs)[i] = reinterpret_cast<const float4*>(w.WgTcan)[i];
+  if (HIDDEN)
+    for (int i = tid; i < 4096; i += 512) reinterpret_cast<float4*>(WBs)[i] = reinterpret_cast<const float4*>(w.W2Tcan)[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tptr + (uint32_t)g * 256u;
+  const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+  constexpr uint32_t COL_H = 0, COL_D = 128, COL_G = 192;  // D: ghid of the current branch; G: gang accumulator
+  const uint32_t wa_addr = s_u32(WAs), wb_addr = s_u32(WBs);
+  uint32_t phase = 0;
+
+  const int64_t ntiles = (a.A + 127) / 128;
+  for (int64_t t = 2 * (int64_t)blockIdx.x + g; t < ntiles; t += 2 * (int64_t)gridDim.x) {
+    const int64_t r0 = t * 128;
+    const int nvalid = (int)min((int64_t)128, a.A - r0);
+    if (gt < 128) {
+      int ia = -1, ib = -1, ic = -1;
+      if (gt < nvalid) {
+        ia = a.a_in[r0 + gt];
+        ib = a.a_out[r0 + gt];
+        ic = a.a_ctr[r0 + gt];
+      }
+      s_a[gt] = ia;
+      s_b[gt] = ib;
+      s_c[gt] = ic;
+    }
+    gbar(g);
+    const bool valid = r < nvalid;
+    const int ib = s_b[r];
+    const size_t row = (size_t)(valid ? r0 + r : 0);
+    const float* uvrow = a.uv + row * D2;
+    const float* gmrow = HIDDEN ? a.gaggB + (size_t)(valid ? ib : 0) * D : a.gang + row * D;
+#pragma unroll 1
+    for (int br = 0; br < 2; br++) {
+      float gp[32];
+      const int cb = br * 64 + c0;
+      if (br == 1) {  // H is still being read by the previous branch's gang GEMM
+        mbar_wait_(&mbar[2], phase);
+        tc_fence_after();
+      }
+      // g for this branch
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int c = c0 + ch * 16 + i * 4;
+          const float4 u4 = *reinterpret_cast<const float4*>(uvrow + c);
+          const float4 v4 = *reinterpret_cast<const float4*>(uvrow + 64 + c);
+          const float4 g4 = *reinterpret_cast<const float4*>(gmrow + c);
+          const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float su = sigm_(uu[j]), oG = sigm_(vv[j]);
+            float gval;
+            if (br == 0)
+              gval = gg[j] * oG * (su * (1.f + uu[j] * (1.f - su)));
+            else
+              gval = gg[j] * (uu[j] * su) * oG * (1.f - oG);
+            if (!valid) gval = 0.f;
+            gp[ch * 16 + 4 * i + j] = gval;
+            const uint32_t h = tf32_hi_bits(gval);
+            hi[4 * i + j] = h;
+            lo[4 * i + j] = __float_as_uint(gval - __uint_as_float(h));
+          }
+        }
+        if (HIDDEN) {
+          tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
+          tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
+        }
+      }
+      if (HIDDEN) {
+        tc_wait_st();
+        tc_fence_before();
+        gbar(g);
+        if (gt == 0) {  // ghid (64 cols) = g . W2_br
+          tc_fence_after();
+          uint32_t acc = 0;
+#pragma unroll
+          for (int term = 0; term < 3; term++) {
+            const uint32_t acol = term == 1 ? 64u : 0u;
+            const uint32_t bsel = wb_addr + (uint32_t)(br * 2 + (term == 2 ? 1 : 0)) * 4096u * 4u;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+              umma_ts(tbase + COL_D, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 2048u, 1024u, 128u), kIdescN64, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(&mbar[br]);
+        }
+        mbar_wait_(&mbar[br], phase);
+        tc_fence_after();
+        const float* dsrow = a.ds + row * D2 + cb;
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          uint32_t v[16];
+          tmem_ld16(tlane + COL_D + c0 + ch * 16, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dsrow + ch * 16 + i * 4);
+            gp[ch * 16 + 4 * i] = __uint_as_float(v[4 * i]) * d4.x;
+            gp[ch * 16 + 4 * i + 1] = __uint_as_float(v[4 * i + 1]) * d4.y;
+            gp[ch * 16 + 4 * i + 2] = __uint_as_float(v[4 * i + 2]) * d4.z;
+            gp[ch * 16 + 4 * i + 3] = __uint_as_float(v[4 * i + 3]) * d4.w;
+          }
+        }
+      }
+      // gpre (32 cols of this branch) -> TMEM operand, then gang += gpre . Wg_br
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const float x = valid ? gp[ch * 16 + i] : 0.f;
+          const uint32_t h = tf32_hi_bits(x);
+          hi[i] = h;
+          lo[i] = __float_as_uint(x - __uint_as_float(h));
+        }
+        tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
+        tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      gbar(g);
+      if (gt == 0) {
+        tc_fence_after();
+        uint32_t acc = br == 0 ? 0u : 1u;
+#pragma unroll
+        for (int term = 0; term < 3; term++) {
+          const uint32_t acol = term == 1 ? 64u : 0u;
+          const uint32_t bsel = wa_addr + (uint32_t)(br * 2 + (term == 2 ? 1 : 0)) * 4096u * 4u;
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) {
+            umma_ts(tbase + COL_G, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 2048u, 1024u, 128u), kIdescN64, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&mbar[2 + br]);
+      }
+      // scatter gpre of this branch: Sigma_b -> gHb, Sigma_c -> gXc (runs), RED -> gHa
+#pragma unroll 1
+      for (int hp = 0; hp < 2; hp++) {
+        if ((q >> 1) == hp) {
+          const int rr = r - hp * 64;
+#pragma unroll
+          for (int i = 0; i < 32; i++) stage[rr * 65 + c0 + i] = gp[i];
+        }
+        gbar(g);
+        {
+          const int c = gt & 63, part = gt >> 6;
+          const int col = br * 64 + c;
+          float sb = 0.f, sc = 0.f;
+          int curb = -1, curc = -1;
+          const int rbeg = part * 16;
+          for (int rr = rbeg; rr < rbeg + 16; rr++) {
+            const int rowi = hp * 64 + rr;
+            const int kb = s_b[rowi], kc = s_c[rowi];
+            const float val = stage[rr * 65 + c];
+            if (kb != curb) {
+              if (curb >= 0) atomicAdd(&a.gHb[(size_t)curb * D2 + col], sb);
+              curb = kb;
+              sb = 0.f;
+            }
+            if (kc != curc) {
+              if (curc >= 0) atomicAdd(&a.gXc[(size_t)curc * D2 + col], sc);
+              curc = kc;
+              sc = 0.f;
+            }
+            if (kb >= 0) {
+              sb += val;
+              sc += val;
+              atomicAdd(&a.gHa[(size_t)s_a[rowi] * D2 + col], val);
+            }
+          }
+          if (curb >= 0) atomicAdd(&a.gHb[(size_t)curb * D2 + col], sb);
+          if (curc >= 0) atomicAdd(&a.gXc[(size_t)curc * D2 + col], sc);
+        }
+        gbar(g);
+      }
+    }
+    mbar_wait_(&mbar[3], phase);
+    tc_fence_after();
+    {
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t v[16];
+        tmem_ld16(tlane + COL_G + c0 + ch * 16, v);
+        tc_wait_ld();
+        if (valid) {
+          float4* pg = reinterpret_cast<float4*>(a.gang + (size_t)(r0 + r) * D + c0 + ch * 16);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            float4 o = pg[i];
+            o.x += __uint_as_float(v[4 * i]), o.y += __uint_as_float(v[4 * i + 1]);
+            o.z += __uint_as_float(v[4 * i + 2]), o.w += __uint_as_float(v[4 * i + 3]);
+            pg[i] = o;
+          }
+        }
+      }
+    }
+    phase ^= 1;
+    tc_fence_before();
+    gbar(g);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if ((tid >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tptr), "r"(512u));
+}
+
+void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms) {
+  if (a.A <= 0) return;
+  static bool attr = false;
+  if (!attr) {
+    B2M_CK(cudaFuncSetAttribute(k_line_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_line_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
+    attr = true;
+  }
+  const int64_t ntiles = (a.A + 127) / 128;
+  const int grid = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
+  if (hidden)
+    k_line_fwd_tc<true><<<grid, 512, LineTcSmem::bytes, st>>>(a, w);
+  else
+    k_line_fwd_tc<false><<<grid, 512, LineTcSmem::bytes, st>>>(a, w);
+  B2M_CK(cudaGetLastError());
+  g_launch_count++;
+}
+void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms) {
+  if (a.A <= 0) return;
+  static bool attr = false;
+  if (!attr) {
+    B2M_CK(cudaFuncSetAttribute(k_line_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_line_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
+    attr = true;
+  }
+  const int64_t ntiles = (a.A + 127) / 128;
+  const int grid = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
+  if (hidden)
+    k_line_bwd_tc<true><<<grid, 512, LineTcSmem::bytes, st>>>(a, w);
+  else
+    k_line_bwd_tc<false><<<grid, 512, LineTcSmem::bytes, st>>>(a, w);
+  B2M_CK(cudaGetLastError());
+  g_launch_count++;
+}
+
+}  // namespace b2m
