@@ -113,6 +113,7 @@ struct b2m_engine {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gather_ev;
   long long launches_last = 0;
   double last_energy = 0;
+  std::map<const float*, const float*> canon_of;  // FFMA-layout GEMM operand -> canonical tcgen05 copy
   int num_sms = 148;
   bool use_tc = true;  // tcgen05 kernels; B2M_LEGACY_FFMA=1 selects the FP32-FFMA tile kernels (A/B checks)
 };
@@ -206,7 +207,26 @@ static void finalize_weights(b2m_engine* e) {
   }
   Packer P;
   std::map<std::string, size_t> off;
-  auto put = [&](const std::string& name, const std::vector<float>& v) { off[name] = P.add(v); };
+  std::vector<std::string> gemm_names;
+  // every [K][N] row-major GEMM operand also gets a tcgen05 copy: canonical hi/lo planes of its [N][K] view
+  auto put = [&](const std::string& name, const std::vector<float>& v) {
+    off[name] = P.add(v);
+    const bool is_k = name.size() > 2 && name.substr(name.size() - 2) == "_k";
+    const bool is_raw = name.size() > 4 && name.substr(name.size() - 4) == "_raw";
+    const bool is_f = name == "F0k" || name == "F1k" || name == "F0raw" || name == "F1raw";
+    if ((is_k || is_raw || is_f) && name.find("Wg_k") == std::string::npos && name.find("WAg_k") == std::string::npos) {
+      int K = 0, N = 0;
+      if (v.size() == 64 * 64) K = 64, N = 64;
+      else if (v.size() == 64 * 128) {
+        // "_k" arrays of the first layers are [64][128]; "_raw" first-layer blocks are [128][64]
+        if (is_raw) K = 128, N = 64; else K = 64, N = 128;
+      }
+      if (K) {
+        off[name + ".can"] = P.add(canon_split(transpose(v, K, N), N, K, K));
+        gemm_names.push_back(name);
+      }
+    }
+  };
 
   const auto& f2 = W(e, "bond_expansion.frequencies", {NR});
   const auto& f3 = W(e, "threebody_bond_expansion.frequencies", {NR});
@@ -346,6 +366,8 @@ static void finalize_weights(b2m_engine* e) {
   B2M_CK(cudaMemcpyAsync(e->wbuf.p, P.host.data(), P.host.size() * sizeof(float), cudaMemcpyHostToDevice, e->st));
   B2M_CK(cudaStreamSynchronize(e->st));
   auto dp = [&](const std::string& n) { return e->wbuf.p + off.at(n); };
+  e->canon_of.clear();
+  for (auto& n : gemm_names) e->canon_of[dp(n)] = dp(n + ".can");
   e->d_fa = dp("fa");
   e->d_emb = dp("emb");
   e->d_Wbe = dp("Wbe");
@@ -381,6 +403,19 @@ static void finalize_weights(b2m_engine* e) {
     w.WAgcan = dp(q + "WAgcan"), w.WAgTcan = dp(q + "WAgTcan");
   }
   e->finalized = true;
+}
+
+// node-level GEMM dispatch: tcgen05 when a canonical copy of B exists, FFMA tile kernel otherwise
+static void gemm(b2m_engine* e, const float* A, int lda, const float* B, float* C, int ldc, int M, int N, int K,
+                 const float* bias, const float* R, int ldr, bool accum) {
+  if (e->use_tc) {
+    auto it = e->canon_of.find(B);
+    if (it != e->canon_of.end()) {
+      launch_gemm_tc(e->st, A, lda, it->second, C, ldc, M, N, K, bias, R, ldr, accum, e->num_sms);
+      return;
+    }
+  }
+  gemm(e, A, lda, B, C, ldc, M, N, K, bias, R, ldr, accum);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -493,9 +528,9 @@ static AtomConvArgs atom_args(b2m_engine* e, int l) {
 static void atom_projections(b2m_engine* e, int l) {
   Graph& g = e->g;
   const AtomLayerW& w = e->aw[l];
-  launch_gemm(e->st, e->x[l].p, D, w.W1s_k, e->Ap.p, D2, g.n_loc, D2, D, nullptr, nullptr, 0, false);
-  launch_gemm(e->st, e->x[l].p, D, w.W1t_k, e->Cp.p, D2, g.n_own, D2, D, w.b1, nullptr, 0, false);
-  if (l > 0) launch_gemm(e->st, e->h[l].p, D, w.W1e_k, e->Qp.p, D2, g.B_own, D2, D, nullptr, nullptr, 0, false);
+  gemm(e, e->x[l].p, D, w.W1s_k, e->Ap.p, D2, g.n_loc, D2, D, nullptr, nullptr, 0, false);
+  gemm(e, e->x[l].p, D, w.W1t_k, e->Cp.p, D2, g.n_own, D2, D, w.b1, nullptr, 0, false);
+  if (l > 0) gemm(e, e->h[l].p, D, w.W1e_k, e->Qp.p, D2, g.B_own, D2, D, nullptr, nullptr, 0, false);
 }
 static void atom_layer_fwd(b2m_engine* e, int l) {
   Graph& g = e->g;
@@ -517,13 +552,13 @@ static void atom_layer_fwd(b2m_engine* e, int l) {
   }
   B2M_CK(cudaEventRecord(e1, e->st));
   e->gather_ev.push_back({e0, e1});
-  launch_gemm(e->st, e->agg.p, D, w.Wout_k, e->x[l + 1].p, D, g.n_own, D, D, nullptr, e->x[l].p, D, false);
+  gemm(e, e->agg.p, D, w.Wout_k, e->x[l + 1].p, D, g.n_own, D, D, nullptr, e->x[l].p, D, false);
 }
 // in: gx = dE/dx[l+1] (owned rows valid, halo rows zero).  out: gx = dE/dx[l] (all local rows)
 static void atom_layer_bwd(b2m_engine* e, int l) {
   Graph& g = e->g;
   const AtomLayerW& w = e->aw[l];
-  launch_gemm(e->st, e->gx.p, D, w.Wout_raw, e->gagg.p, D, g.n_own, D, D, nullptr, nullptr, 0, false);
+  gemm(e, e->gx.p, D, w.Wout_raw, e->gagg.p, D, g.n_own, D, D, nullptr, nullptr, 0, false);
   atom_projections(e, l);
   AtomConvArgs a = atom_args(e, l);
   a.gagg = e->gagg.p;
@@ -542,9 +577,9 @@ static void atom_layer_bwd(b2m_engine* e, int l) {
     launch_atomconv_bwd(e->st, a);
   }
   if (need_gx) {
-    launch_gemm(e->st, e->gA.p, D2, w.W1s_raw, e->gx.p, D, g.n_loc, D, D2, nullptr, nullptr, 0, true);
-    launch_gemm(e->st, e->gC.p, D2, w.W1t_raw, e->gx.p, D, g.n_own, D, D2, nullptr, nullptr, 0, true);
-    launch_gemm(e->st, e->gQ.p, D2, w.W1e_raw, e->gh.p, D, g.B_own, D, D2, nullptr, nullptr, 0, true);
+    gemm(e, e->gA.p, D2, w.W1s_raw, e->gx.p, D, g.n_loc, D, D2, nullptr, nullptr, 0, true);
+    gemm(e, e->gC.p, D2, w.W1t_raw, e->gx.p, D, g.n_own, D, D2, nullptr, nullptr, 0, true);
+    gemm(e, e->gQ.p, D2, w.W1e_raw, e->gh.p, D, g.B_own, D, D2, nullptr, nullptr, 0, true);
   }
 }
 
@@ -589,10 +624,10 @@ static void line_projections(b2m_engine* e, int l, bool hidden) {
   Graph& g = e->g;
   const BondLayerW& w = e->bw[l];
   const float* hsrc = hidden ? e->h[l].p : e->h[l + 1].p;
-  launch_gemm(e->st, hsrc, D, hidden ? w.W1a_k : w.WAa_k, e->Ha.p, D2, g.B_loc, D2, D, nullptr, nullptr, 0, false);
-  launch_gemm(e->st, hsrc, D, hidden ? w.W1b_k : w.WAb_k, e->Hb.p, D2, g.B_own, D2, D, hidden ? w.b1 : w.bA, nullptr,
+  gemm(e, hsrc, D, hidden ? w.W1a_k : w.WAa_k, e->Ha.p, D2, g.B_loc, D2, D, nullptr, nullptr, 0, false);
+  gemm(e, hsrc, D, hidden ? w.W1b_k : w.WAb_k, e->Hb.p, D2, g.B_own, D2, D, hidden ? w.b1 : w.bA, nullptr,
               0, false);
-  launch_gemm(e->st, e->x[l + 1].p, D, hidden ? w.W1c_k : w.WAc_k, e->Xc.p, D2, g.n_loc, D2, D, nullptr, nullptr, 0,
+  gemm(e, e->x[l + 1].p, D, hidden ? w.W1c_k : w.WAc_k, e->Xc.p, D2, g.n_loc, D2, D, nullptr, nullptr, 0,
               false);
 }
 static void line_bwd_common(b2m_engine* e, int l, bool hidden, LineArgs& a) {
@@ -606,9 +641,9 @@ static void line_bwd_common(b2m_engine* e, int l, bool hidden, LineArgs& a) {
     launch_line_bwd_tc(e->st, a, line_tcw(e, l, hidden), hidden, e->num_sms);
   else
     launch_line_bwd(e->st, a, hidden);
-  launch_gemm(e->st, e->gHa.p, D2, hidden ? w.W1a_raw : w.WAa_raw, e->gh.p, D, g.B_loc, D, D2, nullptr, nullptr, 0, true);
-  launch_gemm(e->st, e->gHb.p, D2, hidden ? w.W1b_raw : w.WAb_raw, e->gh.p, D, g.B_own, D, D2, nullptr, nullptr, 0, true);
-  launch_gemm(e->st, e->gXc.p, D2, hidden ? w.W1c_raw : w.WAc_raw, e->gx.p, D, g.n_loc, D, D2, nullptr, nullptr, 0, true);
+  gemm(e, e->gHa.p, D2, hidden ? w.W1a_raw : w.WAa_raw, e->gh.p, D, g.B_loc, D, D2, nullptr, nullptr, 0, true);
+  gemm(e, e->gHb.p, D2, hidden ? w.W1b_raw : w.WAb_raw, e->gh.p, D, g.B_own, D, D2, nullptr, nullptr, 0, true);
+  gemm(e, e->gXc.p, D2, hidden ? w.W1c_raw : w.WAc_raw, e->gx.p, D, g.n_loc, D, D2, nullptr, nullptr, 0, true);
 }
 
 static void forward(b2m_engine* e) {
@@ -626,7 +661,7 @@ static void forward(b2m_engine* e) {
     LineArgs a = line_args(e, l, true);
     a.aggB = e->aggB.p;
     line_fwd_dispatch(e, l, true, a);
-    launch_gemm(e->st, e->aggB.p, D, w.Wout_k, e->upd[l].p, D, g.B_own, D, D, nullptr, nullptr, 0, false);
+    gemm(e, e->aggB.p, D, w.Wout_k, e->upd[l].p, D, g.B_own, D, D, nullptr, nullptr, 0, false);
     launch_bond_update_fwd(e->st, g.B_own, g.b_vec.p, e->rp3, e->d_W3bw, e->h[l].p, e->upd[l].p, e->h[l + 1].p);
     if (l < nb - 2) {
       // the last block's angle update (and the halo copy of h feeding it) is dead code in the
@@ -642,9 +677,9 @@ static void forward(b2m_engine* e) {
   launch_rowdot(e->st, g.n_own, e->x[nb - 1].p, e->d_Ws, e->bs, e->site.p, nullptr, nullptr, nullptr, 1.f);
   atom_layer_fwd(e, nb - 1);
   // final MLP 64 -> 64 -> 64 -> 1, sum (chgnet.py:422-440); E = std * E + mean (+ element refs) (pes.py:109-113)
-  launch_gemm(e->st, e->x[nb].p, D, e->d_F0k, e->y1p.p, D, g.n_own, D, D, e->d_c0, nullptr, 0, false);
+  gemm(e, e->x[nb].p, D, e->d_F0k, e->y1p.p, D, g.n_own, D, D, e->d_c0, nullptr, 0, false);
   launch_silu(e->st, (int64_t)g.n_own * D, e->y1p.p, e->y1.p);
-  launch_gemm(e->st, e->y1.p, D, e->d_F1k, e->y2p.p, D, g.n_own, D, D, e->d_c1, nullptr, 0, false);
+  gemm(e, e->y1.p, D, e->d_F1k, e->y2p.p, D, g.n_own, D, D, e->d_c1, nullptr, 0, false);
   launch_silu(e->st, (int64_t)g.n_own * D, e->y2p.p, e->y2.p);
   B2M_CK(cudaMemsetAsync(e->scal.p, 0, 16 * sizeof(double), e->st));
   launch_rowdot(e->st, g.n_own, e->y2.p, e->d_F2, e->c2, e->e_atom.p, e->scal.p, g.type.p, e->d_eref,
@@ -663,9 +698,9 @@ static void backward(b2m_engine* e) {
   launch_zero_rows(e->st, e->forces.p, g.N * 3);
   // readout backward
   launch_readout_seed(e->st, g.n_own, e->y2p.p, e->d_F2, (float)e->desc.data_std, e->gy2.p);
-  launch_gemm(e->st, e->gy2.p, D, e->d_F1raw, e->gy1.p, D, g.n_own, D, D, nullptr, nullptr, 0, false);
+  gemm(e, e->gy2.p, D, e->d_F1raw, e->gy1.p, D, g.n_own, D, D, nullptr, nullptr, 0, false);
   launch_dsilu_mul(e->st, (int64_t)g.n_own * D, e->y1p.p, e->gy1.p);
-  launch_gemm(e->st, e->gy1.p, D, e->d_F0raw, e->gx.p, D, g.n_own, D, D, nullptr, nullptr, 0, false);
+  gemm(e, e->gy1.p, D, e->d_F0raw, e->gx.p, D, g.n_own, D, D, nullptr, nullptr, 0, false);
   atom_layer_bwd(e, nb - 1);
   for (int l = nb - 2; l >= 0; l--) {
     const BondLayerW& w = e->bw[l];
@@ -676,7 +711,7 @@ static void backward(b2m_engine* e) {
       halo_backward(e, e->gh.p, true);
     }
     launch_bond_update_bwd(e->st, g.B_own, g.b_vec.p, e->rp3, e->d_W3bw, e->gh.p, e->upd[l].p, e->gupd.p, e->gdb.p);
-    launch_gemm(e->st, e->gupd.p, D, w.Wout_raw, e->gaggB.p, D, g.B_own, D, D, nullptr, nullptr, 0, false);
+    gemm(e, e->gupd.p, D, w.Wout_raw, e->gaggB.p, D, g.B_own, D, D, nullptr, nullptr, 0, false);
     line_projections(e, l, true);
     LineArgs a = line_args(e, l, true);
     a.gaggB = e->gaggB.p;

@@ -148,6 +148,10 @@ struct AtomConvTcW {
 };
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
+// C[M,N] = (R | accum C | 0) + A[M,K] @ B + bias, B given as canonical hi/lo planes of its [N][K] view.
+// (K,N) in {(64,128), (64,64), (128,64)}.
+void launch_gemm_tc(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M, int N,
+                    int K, const float* bias, const float* R, int ldr, bool accum, int num_sms);
 struct LineTcW {
   const float* Wgcan;   // [2][8192]: first-layer angle block (N=128, K=64) hi, lo
   const float* W2can;   // [4][4096]: second layers (HIDDEN)

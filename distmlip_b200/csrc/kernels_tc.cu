@@ -1252,3 +1252,152 @@ void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bo
 }
 
 }  // namespace b2m
+
+// ============================================================================================
+// node-level row GEMM on tcgen05 (projections and their transposes): HBM-bound streaming kernel
+// ============================================================================================
+namespace b2m {
+
+template <int K, int N>
+__global__ void __launch_bounds__(256, (2 * K + N <= 256) ? 2 : 1)
+    k_gemm_tc(const float* __restrict__ A, int lda, const float* __restrict__ Bcan, float* __restrict__ C, int ldc, int M,
+              const float* __restrict__ bias, const float* __restrict__ R, int ldr, int accum) {
+  constexpr uint32_t TCOLS = (2 * K + N <= 256) ? 256u : 512u;
+  constexpr uint32_t COL_D = 2 * K;
+  constexpr uint32_t LBO = (N / 8) * 128;
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + 4);
+  float* Bs = smem + 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int r = q * 32 + lane;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(TCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init_(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 2 * N * K / 4; i += 256) reinterpret_cast<float4*>(Bs)[i] = reinterpret_cast<const float4*>(Bcan)[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tptr;
+  const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+  const uint32_t b_addr = s_u32(Bs);
+  uint32_t phase = 0;
+  const int ntiles = (M + 127) / 128;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int row = t * 128 + r;
+    const bool valid = row < M;
+    const float* arow = A + (size_t)(valid ? row : 0) * lda + half * (K / 2);
+#pragma unroll
+    for (int ch = 0; ch < K / 32; ch++) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float4 x = *reinterpret_cast<const float4*>(arow + ch * 16 + i * 4);
+        if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t h = tf32_hi_bits(xv[j]);
+          hi[4 * i + j] = h;
+          lo[4 * i + j] = __float_as_uint(xv[j] - __uint_as_float(h));
+        }
+      }
+      tmem_st16(tlane + half * (K / 2) + ch * 16, hi);
+      tmem_st16(tlane + K + half * (K / 2) + ch * 16, lo);
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      uint32_t acc = 0;
+#pragma unroll
+      for (int term = 0; term < 3; term++) {
+        const uint32_t acol = term == 1 ? (uint32_t)K : 0u;
+        const uint32_t bsel = b_addr + (term == 2 ? (uint32_t)(N * K) * 4u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < K / 8; ks++) {
+          umma_ts(tbase + COL_D, tbase + acol + ks * 8, umma_desc(bsel + ks * 2 * LBO, LBO, 128u), IDESC, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(mbar);
+    }
+    mbar_wait_(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < N / 32; ch++) {
+      uint32_t v[16];
+      const int col = half * (N / 2) + ch * 16;
+      tmem_ld16(tlane + COL_D + col, v);
+      tc_wait_ld();
+      if (valid) {
+        float4* cp = reinterpret_cast<float4*>(C + (size_t)row * ldc + col);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          float4 o = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                 __uint_as_float(v[4 * i + 3]));
+          if (bias) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + col + i * 4);
+            o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+          }
+          if (R) {
+            const float4 rr = *reinterpret_cast<const float4*>(R + (size_t)row * ldr + col + i * 4);
+            o.x += rr.x, o.y += rr.y, o.z += rr.z, o.w += rr.w;
+          }
+          if (accum) {
+            const float4 c = cp[i];
+            o.x += c.x, o.y += c.y, o.z += c.z, o.w += c.w;
+          }
+          cp[i] = o;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(TCOLS));
+}
+
+template <int K, int N>
+static void launch_gemm_tc_t(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M,
+                             const float* bias, const float* R, int ldr, bool accum, int num_sms) {
+  constexpr size_t bytes = (size_t)(64 + 2 * N * K) * 4;
+  static bool attr = false;
+  if (!attr) {
+    B2M_CK(cudaFuncSetAttribute(k_gemm_tc<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    attr = true;
+  }
+  const int ntiles = (M + 127) / 128;
+  const int per_sm = (2 * K + N <= 256) ? 2 : 1;
+  const int grid = std::min(ntiles, per_sm * num_sms);
+  k_gemm_tc<K, N><<<grid, 256, bytes, st>>>(A, lda, Bcan, C, ldc, M, bias, R, ldr, accum ? 1 : 0);
+  B2M_CK(cudaGetLastError());
+  g_launch_count++;
+}
+
+void launch_gemm_tc(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M, int N, int K,
+                    const float* bias, const float* R, int ldr, bool accum, int num_sms) {
+  if (M <= 0) return;
+  if (K == 64 && N == 128)
+    launch_gemm_tc_t<64, 128>(st, A, lda, Bcan, C, ldc, M, bias, R, ldr, accum, num_sms);
+  else if (K == 64 && N == 64)
+    launch_gemm_tc_t<64, 64>(st, A, lda, Bcan, C, ldc, M, bias, R, ldr, accum, num_sms);
+  else if (K == 128 && N == 64)
+    launch_gemm_tc_t<128, 64>(st, A, lda, Bcan, C, ldc, M, bias, R, ldr, accum, num_sms);
+  else
+    throw Error(B2M_ERR_INVALID, "gemm_tc shape");
+}
+
+}  // namespace b2m
