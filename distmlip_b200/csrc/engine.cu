@@ -102,6 +102,7 @@ struct b2m_engine {
   Graph g;
   bool have_graph = false;
   std::vector<DBuf<float>> x, h, ang, upd, uv, uvB, dsB, uvA;
+  DBuf<float> be_e, dbe_e;  // [E,12] radial basis and derivative, once per step
   bool want_grads = true;
   DBuf<float> Ap, Cp, Qp, Ha, Hb, Xc, agg, aggB, y1p, y1, y2p, y2, e_atom, site;
   DBuf<float> gx, gh, gang, gA, gC, gQ, gHa, gHb, gXc, gagg, gupd, gaggB, gd, gdb, gbvec, gy1, gy2;
@@ -437,6 +438,7 @@ static void alloc_workspace(b2m_engine* e) {
     for (auto& b : e->uv) b.ensure(E * D2 + 64);  // second-layer pre-activations kept for the backward
   e->uvB.resize(nb - 1), e->dsB.resize(nb - 1), e->uvA.resize(nb - 1);
   if (e->use_tc) {
+    e->be_e.ensure(E * 12 + 64), e->dbe_e.ensure(E * 12 + 64);
     for (auto& b : e->uvB) b.ensure(A * D2 + 64);
     for (auto& b : e->dsB) b.ensure(A * D2 + 64);
     for (int l = 0; l < nb - 2; l++) e->uvA[l].ensure(A * D2 + 64);
@@ -523,6 +525,7 @@ static AtomConvArgs atom_args(b2m_engine* e, int l) {
   a.Aproj = e->Ap.p, a.Cproj = e->Cp.p, a.Qproj = l > 0 ? e->Qp.p : nullptr;
   a.M = w.M, a.W2k = w.W2k, a.W2raw = w.W2raw, a.b2 = w.b2, a.Wabw = e->d_Wabw;
   a.rp = e->rp2;
+  a.be = e->be_e.p, a.dbe = e->dbe_e.p;
   return a;
 }
 static void atom_projections(b2m_engine* e, int l) {
@@ -649,6 +652,7 @@ static void line_bwd_common(b2m_engine* e, int l, bool hidden, LineArgs& a) {
 static void forward(b2m_engine* e) {
   Graph& g = e->g;
   const int nb = e->desc.n_blocks;
+  if (e->use_tc) launch_edge_basis(e->st, g.E, g.e_vec.p, e->rp2, e->be_e.p, e->dbe_e.p);
   launch_embed(e->st, g.n_loc, g.type.p, e->d_emb, e->x[0].p);
   launch_bond_init(e->st, g.B_loc, g.b_vec.p, e->rp2, e->d_Wbe, e->h[0].p);
   launch_angle_init(e->st, g.A, g.a_in.p, g.a_out.p, g.b_vec.p, e->d_fa, e->d_Wae, e->ang[0].p);

@@ -64,7 +64,10 @@ struct AtomConvArgs {
   // tcgen05 path: second-layer pre-activations (u | v) saved by the forward for the backward
   float* uv_save;       // [E,128] or nullptr (forward)
   const float* uv;      // [E,128] (backward)
+  const float* be;      // [E,12] radial basis (9 used), computed once per step by launch_edge_basis
+  const float* dbe;     // [E,12] d(be)/dd
 };
+void launch_edge_basis(cudaStream_t st, int64_t E, const float4* e_vec, RadialParams rp, float* be, float* dbe);
 void launch_atomconv_fwd(cudaStream_t st, const AtomConvArgs& a);
 void launch_atomconv_bwd(cudaStream_t st, const AtomConvArgs& a);
 

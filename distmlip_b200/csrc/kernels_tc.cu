@@ -92,6 +92,48 @@ __device__ __forceinline__ float rbf_env_val(float d, float freq, const RadialPa
 constexpr uint32_t kIdescN64 = (1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24);
 constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | (16u << 17) | (8u << 24);
 
+__device__ __forceinline__ void rbf_env_both(float d, float freq, const RadialParams& rp, float& be, float& dbe) {
+  const float invd = 1.f / d;
+  const float wq = freq / rp.rc;
+  float s, c;
+  sincosf(d * wq, &s, &c);
+  const float rbf = rp.norm * s * invd;
+  const float drbf = rp.norm * (wq * c * invd - s * invd * invd);
+  const int p = rp.p;
+  const float c1 = -(p + 1) * (p + 2) * 0.5f, c2 = (float)(p * (p + 2)), c3 = -p * (p + 1) * 0.5f;
+  const float rho = rbf / rp.rc;
+  const float rm1 = ipow_(rho, p - 1);
+  const float r0 = rm1 * rho, r1 = r0 * rho, r2 = r1 * rho;
+  const float env = 1.f + c1 * r0 + c2 * r1 + c3 * r2;
+  const float denv = (c1 * p * rm1 + c2 * (p + 1) * r0 + c3 * (p + 2) * r1) / rp.rc;
+  const bool ok = rbf <= rp.rc;
+  be = ok ? env * rbf : 0.f;
+  dbe = ok ? (env + rbf * denv) * drbf : 0.f;
+}
+
+// be[e][0..8], dbe[e][0..8] (padded to 12) for every edge: the same radial basis feeds all atom-conv layers
+__global__ void k_edge_basis(int64_t E, const float4* __restrict__ e_vec, RadialParams rp, float* __restrict__ be,
+                             float* __restrict__ dbe) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= E * 3) return;
+  const int64_t e = i / 3;
+  const int part = (int)(i % 3);
+  const float d = e_vec[e].w;
+  float b[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < 4; j++) {
+    const int k = part * 4 + j;
+    if (k < 9) rbf_env_both(d, rp.freq[k], rp, b[j], db[j]);
+  }
+  reinterpret_cast<float4*>(be)[i] = make_float4(b[0], b[1], b[2], b[3]);
+  reinterpret_cast<float4*>(dbe)[i] = make_float4(db[0], db[1], db[2], db[3]);
+}
+void launch_edge_basis(cudaStream_t st, int64_t E, const float4* e_vec, RadialParams rp, float* be, float* dbe) {
+  if (E <= 0) return;
+  k_edge_basis<<<cdiv(E * 3, 256), 256, 0, st>>>(E, e_vec, rp, be, dbe);
+  B2M_CK(cudaGetLastError());
+  g_launch_count++;
+}
+
 struct FwdTcSmem {
   // float offsets
   static constexpr int kBar = 0;               // 4 mbarriers + tmem ptr (64 floats reserved)
@@ -173,18 +215,22 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
       s_d[tid] = d;
     }
     __syncthreads();
-    {  // radial basis with the reference's envelope-on-value quirk; 9 values per edge, padded to 12
-      const float d = s_d[r];
-      const int k0 = half ? 5 : 0, k1 = half ? 9 : 5;
-      for (int k = k0; k < k1; k++) be_s[r * 12 + k] = r < nvalid ? rbf_env_val(d, a.rp.freq[k], a.rp) : 0.f;
-      if (half) be_s[r * 12 + 9] = be_s[r * 12 + 10] = be_s[r * 12 + 11] = 0.f;
+    float bek[9];  // radial basis of my row (precomputed once per step: launch_edge_basis)
+    {
+      const float4* bp = reinterpret_cast<const float4*>(a.be + (size_t)(r < nvalid ? e0 + r : 0) * 12);
+      const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2];
+      bek[0] = b0.x, bek[1] = b0.y, bek[2] = b0.z, bek[3] = b0.w, bek[4] = b1.x, bek[5] = b1.y, bek[6] = b1.z,
+      bek[7] = b1.w, bek[8] = b2.x;
+      if (r >= nvalid) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) bek[k] = 0.f;
+      }
     }
-    __syncthreads();
     if (half == 0) {  // be -> TMEM operand (K = 16: 9 values + zero pad), hi in cols 0..15, lo in 16..31
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int k = 0; k < 16; k++) {
-        const float x = k < 12 ? be_s[r * 12 + k] : 0.f;
+        const float x = k < 9 ? bek[k] : 0.f;
         const uint32_t h = tf32_hi_bits(x);
         hi[k] = h;
         lo[k] = __float_as_uint(x - __uint_as_float(h));
@@ -280,9 +326,6 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
     // ---- gate product, shared weights, segmented sum over dst (two half-tiles through smem) ----
     float mv[32];
     {
-      float bek[9];
-#pragma unroll
-      for (int k = 0; k < 9; k++) bek[k] = be_s[r * 12 + k];
 #pragma unroll
       for (int ch = 0; ch < 2; ch++) {
         uint32_t u[16], g[16];
@@ -355,25 +398,6 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
 //   gpre = ghid * silu'(pre) is scattered: segmented sums -> gC[dst], RED -> gA[src], store -> gQ[bond],
 //   and contracted with M and dbe/dd for dE/dd_e.
 // ============================================================================================
-__device__ __forceinline__ void rbf_env_both(float d, float freq, const RadialParams& rp, float& be, float& dbe) {
-  const float invd = 1.f / d;
-  const float wq = freq / rp.rc;
-  float s, c;
-  sincosf(d * wq, &s, &c);
-  const float rbf = rp.norm * s * invd;
-  const float drbf = rp.norm * (wq * c * invd - s * invd * invd);
-  const int p = rp.p;
-  const float c1 = -(p + 1) * (p + 2) * 0.5f, c2 = (float)(p * (p + 2)), c3 = -p * (p + 1) * 0.5f;
-  const float rho = rbf / rp.rc;
-  const float rm1 = ipow_(rho, p - 1);
-  const float r0 = rm1 * rho, r1 = r0 * rho, r2 = r1 * rho;
-  const float env = 1.f + c1 * r0 + c2 * r1 + c3 * r2;
-  const float denv = (c1 * p * rm1 + c2 * (p + 1) * r0 + c3 * (p + 2) * r1) / rp.rc;
-  const bool ok = rbf <= rp.rc;
-  be = ok ? env * rbf : 0.f;
-  dbe = ok ? (env + rbf * denv) * drbf : 0.f;
-}
-
 struct BwdTcSmem {
   static constexpr int kBar = 0;
   static constexpr int kW2T = 64;                  // 4 x 4096
@@ -453,22 +477,20 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
       s_d[tid] = d;
     }
     __syncthreads();
-    {
-      const float d = s_d[r];
-      const int k0 = half ? 5 : 0, k1 = half ? 9 : 5;
-      for (int k = k0; k < k1; k++) {
-        float be = 0.f, dbe = 0.f;
-        if (r < nvalid) rbf_env_both(d, a.rp.freq[k], a.rp, be, dbe);
-        be_s[r * 9 + k] = be;
-        dbe_s[r * 9 + k] = dbe;
-      }
-    }
-    __syncthreads();
     float bek[9], dbek[9];
+    {
+      const size_t eo = (size_t)(r < nvalid ? e0 + r : 0) * 12;
+      const float4* bp = reinterpret_cast<const float4*>(a.be + eo);
+      const float4* dp4 = reinterpret_cast<const float4*>(a.dbe + eo);
+      const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], d0 = dp4[0], d1 = dp4[1], d2 = dp4[2];
+      bek[0] = b0.x, bek[1] = b0.y, bek[2] = b0.z, bek[3] = b0.w, bek[4] = b1.x, bek[5] = b1.y, bek[6] = b1.z,
+      bek[7] = b1.w, bek[8] = b2.x;
+      dbek[0] = d0.x, dbek[1] = d0.y, dbek[2] = d0.z, dbek[3] = d0.w, dbek[4] = d1.x, dbek[5] = d1.y, dbek[6] = d1.z,
+      dbek[7] = d1.w, dbek[8] = d2.x;
+      if (r >= nvalid) {
 #pragma unroll
-    for (int k = 0; k < 9; k++) {
-      bek[k] = be_s[r * 9 + k];
-      dbek[k] = dbe_s[r * 9 + k];
+        for (int k = 0; k < 9; k++) bek[k] = dbek[k] = 0.f;
+      }
     }
     if (half == 0) {
       uint32_t hi[16], lo[16];
@@ -1291,16 +1313,22 @@ __global__ void __launch_bounds__(256, (2 * K + N <= 256) ? 2 : 1)
   const uint32_t b_addr = s_u32(Bs);
   uint32_t phase = 0;
   const int ntiles = (M + 127) / 128;
+  float4 pre[K / 8];  // my half of the A row of the tile about to be issued (software prefetch)
+  {
+    const int row0 = blockIdx.x * 128 + r;
+    const float* ar = A + (size_t)(row0 < M ? row0 : 0) * lda + half * (K / 2);
+#pragma unroll
+    for (int i = 0; i < K / 8; i++) pre[i] = (blockIdx.x < ntiles) ? *reinterpret_cast<const float4*>(ar + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int row = t * 128 + r;
     const bool valid = row < M;
-    const float* arow = A + (size_t)(valid ? row : 0) * lda + half * (K / 2);
 #pragma unroll
     for (int ch = 0; ch < K / 32; ch++) {
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        float4 x = *reinterpret_cast<const float4*>(arow + ch * 16 + i * 4);
+        float4 x = pre[ch * 4 + i];
         if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
         const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -1312,6 +1340,15 @@ __global__ void __launch_bounds__(256, (2 * K + N <= 256) ? 2 : 1)
       }
       tmem_st16(tlane + half * (K / 2) + ch * 16, hi);
       tmem_st16(tlane + K + half * (K / 2) + ch * 16, lo);
+    }
+    {  // prefetch the next tile's slice: overlaps with the MMA wait and the epilogue below
+      const int tn = t + gridDim.x;
+      const int rown = tn * 128 + r;
+      if (tn < ntiles) {
+        const float* ar = A + (size_t)(rown < M ? rown : 0) * lda + half * (K / 2);
+#pragma unroll
+        for (int i = 0; i < K / 8; i++) pre[i] = *reinterpret_cast<const float4*>(ar + i * 4);
+      }
     }
     tc_wait_st();
     tc_fence_before();
