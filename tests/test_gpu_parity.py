@@ -289,3 +289,25 @@ def test_axis_permutation_symmetry(eng, model):
     E2, F2, S2 = run_engine(eng, model, b)
     assert abs(E2 - E1) / len(a) < 2e-7
     assert np.abs(F2 - F1[:, P]).max() < 2e-6 and np.abs(S2 - S1[P][:, P]).max() < 2e-6
+
+
+# ------------------------------------------------------------------ the two kernel generations agree on the device
+def test_tcgen05_and_ffma_paths_agree(model):
+    """default path = tcgen05 (3xTF32 in TMEM); B2M_LEGACY_FFMA=1 selects the FP32-FFMA tile kernels."""
+    atoms = si_diamond(4, seed=23)
+    old = os.environ.get("B2M_LEGACY_FFMA")
+    try:
+        os.environ["B2M_LEGACY_FFMA"] = "1"
+        e_ffma = engine_from_model(model)
+        os.environ["B2M_LEGACY_FFMA"] = "0"
+        e_tc = engine_from_model(model)
+    finally:
+        if old is None:
+            os.environ.pop("B2M_LEGACY_FFMA", None)
+        else:
+            os.environ["B2M_LEGACY_FFMA"] = old
+    E1, F1, S1 = run_engine(e_ffma, model, atoms)
+    E2, F2, S2 = run_engine(e_tc, model, atoms)
+    assert abs(E1 - E2) / len(atoms) < 1e-7 and np.abs(F1 - F2).max() < 1e-6 and np.abs(S1 - S2).max() < 1e-6
+    e_ffma.close()
+    e_tc.close()
