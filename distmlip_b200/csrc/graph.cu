@@ -764,7 +764,6 @@ void Graph::build(cudaStream_t st, int64_t natoms, const double* h_cart, const d
     unsigned char* keys = tmp_flag.p + N;
     LAUNCH1D(k_halo_keys, N, st, N, halo_flag, owner.p, world, keys, tmp_i0.p);
     // sort (key, gid): stable radix sort keeps gid ascending inside each key
-    DBuf<unsigned char> keys_out;
     keys_out.ensure(N);
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys_out.p, tmp_i0.p, tmp_i1.p, (int)N, 0, 8, st);
@@ -849,7 +848,6 @@ void Graph::build(cudaStream_t st, int64_t natoms, const double* h_cart, const d
   if (world > 1) {
     to_list.ensure(n_own + 1);
     int off = 0;
-    DBuf<int> sel_out, nsel;
     sel_out.ensure(N);
     nsel.ensure(4);
     for (int q = 0; q < world; q++) {

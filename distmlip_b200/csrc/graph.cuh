@@ -73,6 +73,8 @@ struct Graph {
   DBuf<char> cub_tmp;
   DBuf<double> red_tmp;
   DBuf<int> e_src_gid;
+  DBuf<unsigned char> keys_out;  // persistent scratch: no cudaMalloc/cudaFree on the per-step path
+  DBuf<int> sel_out, nsel;
 
   void build(cudaStream_t st, int64_t natoms, const double* h_cart, const double* h_lat,
              const int32_t* h_species, const int* h_pbc, double rcut, double rbond, double tol_,

@@ -106,6 +106,24 @@ class CHGNet_Dist:
         self.dist_enabled = True
 
     # ------------------------------------------------------------------ hot path
+    def _species_of(self, atoms):
+        """element index per atom (chgnet.py:66-72), vectorised through atomic numbers when the Atoms object has them"""
+        if hasattr(atoms, "get_atomic_numbers"):
+            lut = self.__dict__.get("_z_lut")
+            if lut is None:
+                from distmlip_b200.structures import Z_OF
+
+                lut = np.full(len(Z_OF) + 1, -1, dtype=np.int32)
+                for el, idx in self.element_to_index.items():
+                    if el in Z_OF:
+                        lut[Z_OF[el]] = idx
+                self._z_lut = lut
+            sp = lut[np.asarray(atoms.get_atomic_numbers())]
+            if (sp < 0).any():
+                raise KeyError("structure contains an element that is not in model.element_types")
+            return sp
+        return np.array([self.element_to_index[s] for s in atoms.get_chemical_symbols()], dtype=np.int32)
+
     def _finalize(self, data_mean, data_std, element_refs):
         eng = self._engine
         key = (float(data_mean), float(data_std), None if element_refs is None else tuple(np.ravel(element_refs)))
@@ -129,7 +147,8 @@ class CHGNet_Dist:
         node_types = torch.as_tensor(dist_info.species, dtype=distmlip_b200.int_th)
         positions = torch.as_tensor(np.asarray(atoms.get_positions(wrap=False)), dtype=distmlip_b200.float_th)
         strain = torch.zeros(1, 3, 3, dtype=distmlip_b200.float_th)
-        site = torch.as_tensor(eng.sitewise()).reshape(-1, 1)
+        # the site-wise readout is only gathered (one more all-reduce) when the Potential asks for it
+        site = torch.as_tensor(eng.sitewise()).reshape(-1, 1) if self.__dict__.get("_want_site", True) else None
         return node_types, positions, strain, (torch.tensor([e], dtype=torch.float64), site)
 
     def dist_forward(self, *args, **kwargs):

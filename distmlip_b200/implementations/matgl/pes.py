@@ -58,7 +58,8 @@ class Potential_Dist:
         cart_coords = np.array(atoms.get_positions(wrap=False))
         pbc = atoms.get_pbc().astype(np.int64)
         model = self.model
-        species = np.array([model.element_to_index[s] for s in atoms.get_chemical_symbols()], dtype=np.int32)
+        species = model._species_of(atoms)
+        model._want_site = bool(self.calc_site_wise)
         model._finalize(self.data_mean, self.data_std, self.element_refs)
         dist_info = Distributed.create_distributed(
             cart_coords=cart_coords, frac_coords=None, lattice_matrix=lattice_matrix,

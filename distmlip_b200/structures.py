@@ -11,6 +11,13 @@ import numpy as np
 
 SI_A = 5.431  # Angstrom, diamond-cubic Si conventional cell
 
+SYMBOLS = (
+    "X H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr Rb Sr Y Zr "
+    "Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu Hf Ta W Re Os Ir Pt "
+    "Au Hg Tl Pb Bi Po At Rn Fr Ra Ac Th Pa U Np Pu Am Cm Bk Cf Es Fm Md No Lr Rf Db Sg Bh Hs Mt Ds Rg Cn Nh Fl Mc Lv "
+    "Ts Og").split()
+Z_OF = {s: z for z, s in enumerate(SYMBOLS)}
+
 _DIAMOND_BASIS = np.array(
     [
         [0.00, 0.00, 0.00],
@@ -62,6 +69,11 @@ class SimpleAtoms:
 
     def get_chemical_symbols(self):
         return list(self._symbols)
+
+    def get_atomic_numbers(self):
+        if getattr(self, "_numbers", None) is None:
+            self._numbers = np.array([Z_OF[s] for s in self._symbols], dtype=np.int64)
+        return self._numbers.copy()
 
     def get_volume(self):
         return float(abs(np.linalg.det(self._cell)))
