@@ -56,7 +56,9 @@ class Distributed:
         if species is None:
             species = np.zeros(len(cart_coords), dtype=np.int32)
         engine.set_structure(cart_coords, lattice_matrix, species, np.asarray(pbc).astype(np.int32), tol)
-        return cls(engine, np.asarray(species), len(cart_coords), use_bond_graph, num_partitions)
+        obj = cls(engine, np.asarray(species), len(cart_coords), use_bond_graph, num_partitions)
+        obj.cart = cart_coords
+        return obj
 
     # ---- counters (dist.py:462-551), for this rank's partition ----
     def num_atoms(self, partition=None):

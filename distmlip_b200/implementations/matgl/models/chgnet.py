@@ -145,7 +145,7 @@ class CHGNet_Dist:
         e, f, s = eng.compute(forces=calc_forces, stress=calc_stresses)
         dist_info.forces, dist_info.stress = f, s
         node_types = torch.as_tensor(dist_info.species, dtype=distmlip_b200.int_th)
-        positions = torch.as_tensor(np.asarray(atoms.get_positions(wrap=False)), dtype=distmlip_b200.float_th)
+        positions = torch.from_numpy(dist_info.cart)  # zero-copy view (f64); no autograd graph hangs off it here
         strain = torch.zeros(1, 3, 3, dtype=distmlip_b200.float_th)
         # the site-wise readout is only gathered (one more all-reduce) when the Potential asks for it
         site = torch.as_tensor(eng.sitewise()).reshape(-1, 1) if self.__dict__.get("_want_site", True) else None

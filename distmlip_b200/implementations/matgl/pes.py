@@ -55,7 +55,7 @@ class Potential_Dist:
         # kept for signature compatibility; the graph build has no host threads
         _ = self.num_threads if self.num_threads else int(os.environ.get("DISTMLIP_NUM_THREADS", 8))
         lattice_matrix = np.array(atoms.get_cell())
-        cart_coords = np.array(atoms.get_positions(wrap=False))
+        cart_coords = np.asarray(atoms.get_positions(wrap=False))  # ASE already returns a copy
         pbc = atoms.get_pbc().astype(np.int64)
         model = self.model
         species = model._species_of(atoms)
