@@ -435,13 +435,14 @@ static void alloc_workspace(b2m_engine* e) {
   for (auto& b : e->upd) b.ensure(bo * D + 64);
   e->uv.resize(nb);
   if (e->use_tc)
-    for (auto& b : e->uv) b.ensure(E * D2 + 64);  // second-layer pre-activations kept for the backward
+    for (auto& b : e->uv) b.ensure(((E + 127) / 128 * 128) * D2 + 64);  // u|v kept for the backward (tile-interleaved)
   e->uvB.resize(nb - 1), e->dsB.resize(nb - 1), e->uvA.resize(nb - 1);
   if (e->use_tc) {
-    e->be_e.ensure(E * 12 + 64), e->dbe_e.ensure(E * 12 + 64);
-    for (auto& b : e->uvB) b.ensure(A * D2 + 64);
-    for (auto& b : e->dsB) b.ensure(A * D2 + 64);
-    for (int l = 0; l < nb - 2; l++) e->uvA[l].ensure(A * D2 + 64);
+    e->be_e.ensure(((E + 127) / 128 * 128) * 12 + 64), e->dbe_e.ensure(((E + 127) / 128 * 128) * 12 + 64);
+    const size_t Ap = (A + 127) / 128 * 128;
+    for (auto& b : e->uvB) b.ensure(Ap * D2 + 64);
+    for (auto& b : e->dsB) b.ensure(Ap * D2 + 64);
+    for (int l = 0; l < nb - 2; l++) e->uvA[l].ensure(Ap * D2 + 64);
   }
   e->Ap.ensure(nl * D2 + 64), e->Cp.ensure(no * D2 + 64), e->Qp.ensure(bo * D2 + 64);
   e->Ha.ensure(bl * D2 + 64), e->Hb.ensure(bo * D2 + 64), e->Xc.ensure(nl * D2 + 64);

@@ -88,6 +88,14 @@ __device__ __forceinline__ float rbf_env_val(float d, float freq, const RadialPa
   return rbf <= rp.rc ? env * rbf : 0.f;
 }
 
+// Tile-interleaved layout of kernel-private row tensors ([rows][W] logically, W = 4*NC4 floats):
+//   float4 index ((tile * NC4 + c/4) * 128 + r)  ->  a warp's thread=row access touches 512 contiguous bytes
+// instead of 32 different cache lines (the LSU wavefront count of the row-major layout was the bottleneck).
+template <int NC4>
+__device__ __forceinline__ size_t tl4(int64_t tile, int r, int c) {
+  return ((size_t)(tile * NC4 + (c >> 2)) * 128 + r);
+}
+
 // instruction descriptors: c=F32, a=b=TF32, K-major, M=128
 constexpr uint32_t kIdescN64 = (1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24);
 constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | (16u << 17) | (8u << 24);
@@ -124,8 +132,9 @@ __global__ void k_edge_basis(int64_t E, const float4* __restrict__ e_vec, Radial
     const int k = part * 4 + j;
     if (k < 9) rbf_env_both(d, rp.freq[k], rp, b[j], db[j]);
   }
-  reinterpret_cast<float4*>(be)[i] = make_float4(b[0], b[1], b[2], b[3]);
-  reinterpret_cast<float4*>(dbe)[i] = make_float4(db[0], db[1], db[2], db[3]);
+  const size_t o = tl4<3>(e >> 7, (int)(e & 127), part * 4);
+  reinterpret_cast<float4*>(be)[o] = make_float4(b[0], b[1], b[2], b[3]);
+  reinterpret_cast<float4*>(dbe)[o] = make_float4(db[0], db[1], db[2], db[3]);
 }
 void launch_edge_basis(cudaStream_t st, int64_t E, const float4* e_vec, RadialParams rp, float* be, float* dbe) {
   if (E <= 0) return;
@@ -149,7 +158,13 @@ struct FwdTcSmem {
   static constexpr size_t bytes = (size_t)kTotal * 4;
 };
 
-__global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a, const AtomConvTcW w) {
+// NTHR = 256: two threads per row (32 columns of each branch per thread, <=128 registers);
+// NTHR = 512: four threads per row (16 columns, <=64 registers) -> twice the resident warps for the same TMEM/smem.
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, 2) k_atomconv_fwd_tc(const AtomConvArgs a, const AtomConvTcW w) {
+  constexpr int NP = NTHR / 128;   // threads per row
+  constexpr int CPT = 64 / NP;     // columns of each branch per thread
+  constexpr int NCH = CPT / 16;    // 16-column chunks per thread
   extern __shared__ __align__(1024) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + FwdTcSmem::kBar);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + FwdTcSmem::kBar + 16);
@@ -165,9 +180,9 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
   int* s_bond = s_dst + 128;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, half = warp >> 2;
+  const int q = warp & 3, half = warp >> 2;  // half = column part 0..NP-1
   const int r = q * 32 + lane;   // my row (TMEM lane)
-  const int c0 = half * 32;      // my 32 columns inside each 64-wide branch
+  const int c0 = half * CPT;     // my columns inside each 64-wide branch
   const bool useQ = a.Qproj != nullptr;
 
   // ---- one-time setup: TMEM, barriers, weights ----
@@ -181,9 +196,9 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
     mbar_init_(&mbar[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 4 * 1024; i += 256) reinterpret_cast<float4*>(W2s)[i] = reinterpret_cast<const float4*>(w.W2can)[i];
-  for (int i = tid; i < 2 * 512; i += 256) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
-  for (int i = tid; i < 576; i += 256) wabW[i] = a.Wabw[i];
+  for (int i = tid; i < 4 * 1024; i += NTHR) reinterpret_cast<float4*>(W2s)[i] = reinterpret_cast<const float4*>(w.W2can)[i];
+  for (int i = tid; i < 2 * 512; i += NTHR) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
+  for (int i = tid; i < 576; i += NTHR) wabW[i] = a.Wabw[i];
   if (tid < 128) b2s[tid] = a.b2[tid];
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
@@ -217,8 +232,8 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
     __syncthreads();
     float bek[9];  // radial basis of my row (precomputed once per step: launch_edge_basis)
     {
-      const float4* bp = reinterpret_cast<const float4*>(a.be + (size_t)(r < nvalid ? e0 + r : 0) * 12);
-      const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2];
+      const float4* bp = reinterpret_cast<const float4*>(a.be);
+      const float4 b0 = bp[tl4<3>(t, r, 0)], b1 = bp[tl4<3>(t, r, 4)], b2 = bp[tl4<3>(t, r, 8)];
       bek[0] = b0.x, bek[1] = b0.y, bek[2] = b0.z, bek[3] = b0.w, bek[4] = b1.x, bek[5] = b1.y, bek[6] = b1.z,
       bek[7] = b1.w, bek[8] = b2.x;
       if (r >= nvalid) {
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
       tc_fence_after();
       const int cb = br * 64 + c0;  // column in the 128-wide first layer
 #pragma unroll
-      for (int ch = 0; ch < 2; ch++) {
+      for (int ch = 0; ch < NCH; ch++) {
         uint32_t v[16], hi[16], lo[16];
         tmem_ld16(tlane + COL_D + cb + ch * 16, v);
         tc_wait_ld();
@@ -324,10 +339,10 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
     tc_fence_after();
     phase ^= 1;
     // ---- gate product, shared weights, segmented sum over dst (two half-tiles through smem) ----
-    float mv[32];
+    float mv[CPT];
     {
 #pragma unroll
-      for (int ch = 0; ch < 2; ch++) {
+      for (int ch = 0; ch < NCH; ch++) {
         uint32_t u[16], g[16];
         tmem_ld16(tlane + COL_D + c0 + ch * 16, u);
         tmem_ld16(tlane + COL_D + 64 + c0 + ch * 16, g);
@@ -346,14 +361,13 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
           mv[ch * 16 + i] = valid ? oL * oG * wab : 0.f;
         }
         if (a.uv_save != nullptr && valid) {
-          float4* pu = reinterpret_cast<float4*>(a.uv_save + (size_t)(e0 + r) * D2 + c0 + ch * 16);
-          float4* pv = reinterpret_cast<float4*>(a.uv_save + (size_t)(e0 + r) * D2 + 64 + c0 + ch * 16);
+          float4* puv = reinterpret_cast<float4*>(a.uv_save);
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            pu[i] = make_float4(__uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]), __uint_as_float(u[4 * i + 2]),
-                                __uint_as_float(u[4 * i + 3]));
-            pv[i] = make_float4(__uint_as_float(g[4 * i]), __uint_as_float(g[4 * i + 1]), __uint_as_float(g[4 * i + 2]),
-                                __uint_as_float(g[4 * i + 3]));
+            puv[tl4<32>(t, r, c0 + ch * 16 + 4 * i)] = make_float4(__uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]),
+                                                                  __uint_as_float(u[4 * i + 2]), __uint_as_float(u[4 * i + 3]));
+            puv[tl4<32>(t, r, 64 + c0 + ch * 16 + 4 * i)] = make_float4(__uint_as_float(g[4 * i]), __uint_as_float(g[4 * i + 1]),
+                                                                       __uint_as_float(g[4 * i + 2]), __uint_as_float(g[4 * i + 3]));
           }
         }
       }
@@ -364,15 +378,16 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_fwd_tc(const AtomConvArgs a
       if ((q >> 1) == hp) {
         const int rr = r - hp * 64;
 #pragma unroll
-        for (int i = 0; i < 32; i++) msg[rr * 65 + c0 + i] = mv[i];
+        for (int i = 0; i < CPT; i++) msg[rr * 65 + c0 + i] = mv[i];
       }
       __syncthreads();
       {
-        const int c = tid & 63, part = tid >> 6;  // 4 parts x 16 rows
+        constexpr int RPP = 64 / (NTHR / 64);  // rows per reducing thread
+        const int c = tid & 63, part = tid >> 6;
         float sum = 0.f;
         int cur = -1;
-        const int rbeg = part * 16;
-        for (int rr = rbeg; rr < rbeg + 16; rr++) {
+        const int rbeg = part * RPP;
+        for (int rr = rbeg; rr < rbeg + RPP; rr++) {
           const int k = s_dst[hp * 64 + rr];
           if (k != cur) {
             if (cur >= 0) atomicAdd(&a.agg[(size_t)cur * D + c], sum);
@@ -412,7 +427,11 @@ struct BwdTcSmem {
   static constexpr size_t bytes = (size_t)kTotal * 4;
 };
 
-__global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a, const AtomConvTcW w) {
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs a, const AtomConvTcW w) {
+  constexpr int NP = NTHR / 128;   // threads per row
+  constexpr int CPT = 64 / NP;     // columns of each branch per thread
+  constexpr int NCH = CPT / 16;
   extern __shared__ __align__(1024) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + BwdTcSmem::kBar);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + BwdTcSmem::kBar + 16);
@@ -430,7 +449,7 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;
   const int r = q * 32 + lane;
-  const int c0 = half * 32;
+  const int c0 = half * CPT;
   const bool useQ = a.Qproj != nullptr;
   const bool need_gx = a.gA != nullptr;
 
@@ -444,9 +463,9 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
     mbar_init_(&mbar[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 4 * 1024; i += 256) reinterpret_cast<float4*>(W2Ts)[i] = reinterpret_cast<const float4*>(w.W2Tcan)[i];
-  for (int i = tid; i < 2 * 512; i += 256) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
-  for (int i = tid; i < 576; i += 256) wabW[i] = a.Wabw[i];
+  for (int i = tid; i < 4 * 1024; i += NTHR) reinterpret_cast<float4*>(W2Ts)[i] = reinterpret_cast<const float4*>(w.W2Tcan)[i];
+  for (int i = tid; i < 2 * 512; i += NTHR) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
+  for (int i = tid; i < 576; i += NTHR) wabW[i] = a.Wabw[i];
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -479,10 +498,10 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
     __syncthreads();
     float bek[9], dbek[9];
     {
-      const size_t eo = (size_t)(r < nvalid ? e0 + r : 0) * 12;
-      const float4* bp = reinterpret_cast<const float4*>(a.be + eo);
-      const float4* dp4 = reinterpret_cast<const float4*>(a.dbe + eo);
-      const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], d0 = dp4[0], d1 = dp4[1], d2 = dp4[2];
+      const float4* bp = reinterpret_cast<const float4*>(a.be);
+      const float4* dp4 = reinterpret_cast<const float4*>(a.dbe);
+      const float4 b0 = bp[tl4<3>(t, r, 0)], b1 = bp[tl4<3>(t, r, 4)], b2 = bp[tl4<3>(t, r, 8)];
+      const float4 d0 = dp4[tl4<3>(t, r, 0)], d1 = dp4[tl4<3>(t, r, 4)], d2 = dp4[tl4<3>(t, r, 8)];
       bek[0] = b0.x, bek[1] = b0.y, bek[2] = b0.z, bek[3] = b0.w, bek[4] = b1.x, bek[5] = b1.y, bek[6] = b1.z,
       bek[7] = b1.w, bek[8] = b2.x;
       dbek[0] = d0.x, dbek[1] = d0.y, dbek[2] = d0.z, dbek[3] = d0.w, dbek[4] = d1.x, dbek[5] = d1.y, dbek[6] = d1.z,
@@ -528,7 +547,7 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
     const float* Arow = a.Aproj + (size_t)src * D2;
     const float* Crow = a.Cproj + (size_t)(valid ? dst : 0) * D2;
     const float* Qrow = viaQ ? a.Qproj + (size_t)bond * D2 : nullptr;
-    const float* uvrow = a.uv + (size_t)(valid ? e0 + r : 0) * D2;
+    const float4* uv4 = reinterpret_cast<const float4*>(a.uv);
     const float* gmrow = a.gagg + (size_t)(valid ? dst : 0) * D;
     float gdpart = 0.f;   // dE/dd_e contribution of this thread's columns
     float gbeM[9];
@@ -540,9 +559,9 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
       mbar_wait_(&mbar[br], phase);
       tc_fence_after();
       const int cb = br * 64 + c0;
-      float ds[32];  // silu'(pre) for my 32 columns of this branch
+      float ds[CPT];  // silu'(pre) for my columns of this branch
 #pragma unroll
-      for (int ch = 0; ch < 2; ch++) {
+      for (int ch = 0; ch < NCH; ch++) {
         uint32_t v[16], hi[16], lo[16];
         tmem_ld16(tlane + COL_D + cb + ch * 16, v);
         tc_wait_ld();
@@ -564,8 +583,8 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const int c = c0 + ch * 16 + i * 4;
-          const float4 u4 = *reinterpret_cast<const float4*>(uvrow + c);
-          const float4 v4 = *reinterpret_cast<const float4*>(uvrow + 64 + c);
+          const float4 u4 = uv4[tl4<32>(t, r, c)];
+          const float4 v4 = uv4[tl4<32>(t, r, 64 + c)];
           const float4 g4 = *reinterpret_cast<const float4*>(gmrow + c);
           const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
@@ -620,7 +639,7 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
       tc_fence_after();
       // gpre = ghid * silu'(pre)
 #pragma unroll
-      for (int ch = 0; ch < 2; ch++) {
+      for (int ch = 0; ch < NCH; ch++) {
         uint32_t v[16];
         tmem_ld16(tlane + COL_D + br * 64 + c0 + ch * 16, v);
         tc_wait_ld();
@@ -630,7 +649,7 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
       // dE/d be through the radial first-layer term (not for bond rows fed by Q)
       if (!viaQ) {
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
+        for (int i = 0; i < CPT; i++) {
           const float* Mj = a.M + (size_t)(cb + i) * 9;
 #pragma unroll
           for (int k = 0; k < 9; k++) gbeM[k] = fmaf(ds[i], __ldg(Mj + k), gbeM[k]);
@@ -642,16 +661,17 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
           if ((q >> 1) == hp) {
             const int rr = r - hp * 64;
 #pragma unroll
-            for (int i = 0; i < 32; i++) stage[rr * 65 + c0 + i] = ds[i];
+            for (int i = 0; i < CPT; i++) stage[rr * 65 + c0 + i] = ds[i];
           }
           __syncthreads();
           {
+            constexpr int RPP = 64 / (NTHR / 64);
             const int c = tid & 63, part = tid >> 6;
             const int col = br * 64 + c;
             float sum = 0.f;
             int cur = -1;
-            const int rbeg = part * 16;
-            for (int rr = rbeg; rr < rbeg + 16; rr++) {
+            const int rbeg = part * RPP;
+            for (int rr = rbeg; rr < rbeg + RPP; rr++) {
               const int row = hp * 64 + rr;
               const int k = s_dst[row];
               const float val = stage[rr * 65 + c];
@@ -683,7 +703,12 @@ __global__ void __launch_bounds__(256, 2) k_atomconv_bwd_tc(const AtomConvArgs a
       stage[tid] = valid ? s : 0.f;
       tc_fence_before();
       __syncthreads();
-      if (tid < nvalid) a.gd[e0 + tid] += stage[tid] + stage[128 + tid];
+      if (tid < nvalid) {
+        float tot = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NP; pp++) tot += stage[pp * 128 + tid];
+        a.gd[e0 + tid] += tot;
+      }
       __syncthreads();
     }
   }
@@ -696,12 +721,20 @@ void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
   if (a.E <= 0) return;
   static bool attr = false;
   if (!attr) {
-    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
     attr = true;
   }
   const int64_t ntiles = (a.E + 127) / 128;
   const int grid = (int)std::min<int64_t>(ntiles, 2 * (int64_t)num_sms);
-  k_atomconv_bwd_tc<<<grid, 256, BwdTcSmem::bytes, st>>>(a, w);
+  static const int nthr = [] {
+    const char* v = getenv("B2M_BWD_THREADS");
+    return (v && atoi(v) == 512) ? 512 : 256;  // 512 (4 threads/row, 64 regs) measured slower: LSU-bound, not warp-bound
+  }();
+  if (nthr == 512)
+    k_atomconv_bwd_tc<512><<<grid, 512, BwdTcSmem::bytes, st>>>(a, w);
+  else
+    k_atomconv_bwd_tc<256><<<grid, 256, BwdTcSmem::bytes, st>>>(a, w);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
@@ -710,12 +743,20 @@ void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
   if (a.E <= 0) return;
   static bool attr = false;
   if (!attr) {
-    B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
     attr = true;
   }
   const int64_t ntiles = (a.E + 127) / 128;
   const int grid = (int)std::min<int64_t>(ntiles, 2 * (int64_t)num_sms);
-  k_atomconv_fwd_tc<<<grid, 256, FwdTcSmem::bytes, st>>>(a, w);
+  static const int nthr = [] {
+    const char* v = getenv("B2M_FWD_THREADS");
+    return (v && atoi(v) == 512) ? 512 : 256;  // 512 (4 threads/row, 64 regs) measured slower: LSU-bound, not warp-bound
+  }();
+  if (nthr == 512)
+    k_atomconv_fwd_tc<512><<<grid, 512, FwdTcSmem::bytes, st>>>(a, w);
+  else
+    k_atomconv_fwd_tc<256><<<grid, 256, FwdTcSmem::bytes, st>>>(a, w);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
@@ -875,9 +916,10 @@ __global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const 
             }
           }
           if (a.ds_save != nullptr && valid) {
-            float4* pd = reinterpret_cast<float4*>(a.ds_save + (size_t)(r0 + r) * D2 + cb + ch * 16);
+            float4* pd = reinterpret_cast<float4*>(a.ds_save);
 #pragma unroll
-            for (int i = 0; i < 4; i++) pd[i] = make_float4(dsv[4 * i], dsv[4 * i + 1], dsv[4 * i + 2], dsv[4 * i + 3]);
+            for (int i = 0; i < 4; i++)
+              pd[tl4<32>(t, r, cb + ch * 16 + 4 * i)] = make_float4(dsv[4 * i], dsv[4 * i + 1], dsv[4 * i + 2], dsv[4 * i + 3]);
           }
           tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
           tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
@@ -944,12 +986,11 @@ __global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const 
         }
       }
       if (a.uv_save != nullptr && valid) {
-        float4* pu = reinterpret_cast<float4*>(a.uv_save + (size_t)(r0 + r) * D2 + c0 + ch * 16);
-        float4* pv = reinterpret_cast<float4*>(a.uv_save + (size_t)(r0 + r) * D2 + 64 + c0 + ch * 16);
+        float4* puv = reinterpret_cast<float4*>(a.uv_save);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          pu[i] = make_float4(uf[4 * i], uf[4 * i + 1], uf[4 * i + 2], uf[4 * i + 3]);
-          pv[i] = make_float4(vf[4 * i], vf[4 * i + 1], vf[4 * i + 2], vf[4 * i + 3]);
+          puv[tl4<32>(t, r, c0 + ch * 16 + 4 * i)] = make_float4(uf[4 * i], uf[4 * i + 1], uf[4 * i + 2], uf[4 * i + 3]);
+          puv[tl4<32>(t, r, 64 + c0 + ch * 16 + 4 * i)] = make_float4(vf[4 * i], vf[4 * i + 1], vf[4 * i + 2], vf[4 * i + 3]);
         }
       }
 #pragma unroll
@@ -1058,7 +1099,7 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
     const bool valid = r < nvalid;
     const int ib = s_b[r];
     const size_t row = (size_t)(valid ? r0 + r : 0);
-    const float* uvrow = a.uv + row * D2;
+    const float4* uv4 = reinterpret_cast<const float4*>(a.uv);
     const float* gmrow = HIDDEN ? a.gaggB + (size_t)(valid ? ib : 0) * D : a.gang + row * D;
 #pragma unroll 1
     for (int br = 0; br < 2; br++) {
@@ -1075,8 +1116,8 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const int c = c0 + ch * 16 + i * 4;
-          const float4 u4 = *reinterpret_cast<const float4*>(uvrow + c);
-          const float4 v4 = *reinterpret_cast<const float4*>(uvrow + 64 + c);
+          const float4 u4 = uv4[tl4<32>(t, r, c)];
+          const float4 v4 = uv4[tl4<32>(t, r, 64 + c)];
           const float4 g4 = *reinterpret_cast<const float4*>(gmrow + c);
           const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
@@ -1120,7 +1161,7 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
         }
         mbar_wait_(&mbar[br], phase);
         tc_fence_after();
-        const float* dsrow = a.ds + row * D2 + cb;
+        const float4* ds4 = reinterpret_cast<const float4*>(a.ds);
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
           uint32_t v[16];
@@ -1128,7 +1169,7 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
           tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            const float4 d4 = *reinterpret_cast<const float4*>(dsrow + ch * 16 + i * 4);
+            const float4 d4 = ds4[tl4<32>(t, r, cb + ch * 16 + i * 4)];
             gp[ch * 16 + 4 * i] = __uint_as_float(v[4 * i]) * d4.x;
             gp[ch * 16 + 4 * i + 1] = __uint_as_float(v[4 * i + 1]) * d4.y;
             gp[ch * 16 + 4 * i + 2] = __uint_as_float(v[4 * i + 2]) * d4.z;
