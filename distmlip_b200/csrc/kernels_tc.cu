@@ -1321,23 +1321,28 @@ void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bo
 // ============================================================================================
 namespace b2m {
 
+// A tiles are read and C tiles written COOPERATIVELY (coalesced 512 B per warp instruction) through a padded
+// shared-memory tile [128][68]; the thread=row view needed by tcgen05.st / tcgen05.ld is taken from shared memory
+// (LDS.128 / STS.128 with a 272 B pitch are conflict free).  K = 128 is processed as two accumulating K = 64 halves,
+// so every shape needs 128 (A hi|lo) + N TMEM columns <= 256 and two CTAs share an SM.
 template <int K, int N>
-__global__ void __launch_bounds__(256, (2 * K + N <= 256) ? 2 : 1)
+__global__ void __launch_bounds__(256, 2)
     k_gemm_tc(const float* __restrict__ A, int lda, const float* __restrict__ Bcan, float* __restrict__ C, int ldc, int M,
               const float* __restrict__ bias, const float* __restrict__ R, int ldr, int accum) {
-  constexpr uint32_t TCOLS = (2 * K + N <= 256) ? 256u : 512u;
-  constexpr uint32_t COL_D = 2 * K;
+  constexpr uint32_t COL_D = 128;
   constexpr uint32_t LBO = (N / 8) * 128;
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+  constexpr int PITCH = 68;
   extern __shared__ __align__(1024) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + 4);
   float* Bs = smem + 64;
+  float* stg = Bs + 2 * N * K;  // [128][68]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;
   const int r = q * 32 + lane;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(TCOLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(256u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
@@ -1354,112 +1359,118 @@ __global__ void __launch_bounds__(256, (2 * K + N <= 256) ? 2 : 1)
   const uint32_t b_addr = s_u32(Bs);
   uint32_t phase = 0;
   const int ntiles = (M + 127) / 128;
-  float4 pre[K / 8];  // my half of the A row of the tile about to be issued (software prefetch)
-  {
-    const int row0 = blockIdx.x * 128 + r;
-    const float* ar = A + (size_t)(row0 < M ? row0 : 0) * lda + half * (K / 2);
-#pragma unroll
-    for (int i = 0; i < K / 8; i++) pre[i] = (blockIdx.x < ntiles) ? *reinterpret_cast<const float4*>(ar + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int row = t * 128 + r;
-    const bool valid = row < M;
+    const int row0 = t * 128;
+#pragma unroll 1
+    for (int kh = 0; kh < K / 64; kh++) {
+      // cooperative, coalesced load of A[row0 .. +128, kh*64 .. +64] into the padded tile
 #pragma unroll
-    for (int ch = 0; ch < K / 32; ch++) {
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        float4 x = pre[ch * 4 + i];
-        if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float xv[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t h = tf32_hi_bits(xv[j]);
-          hi[4 * i + j] = h;
-          lo[4 * i + j] = __float_as_uint(xv[j] - __uint_as_float(h));
-        }
+      for (int i = 0; i < 8; i++) {
+        const int idx = tid + 256 * i;
+        const int rr = idx >> 4, c4 = idx & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + rr < M) v = *reinterpret_cast<const float4*>(A + (size_t)(row0 + rr) * lda + kh * 64 + c4 * 4);
+        *reinterpret_cast<float4*>(stg + rr * PITCH + c4 * 4) = v;
       }
-      tmem_st16(tlane + half * (K / 2) + ch * 16, hi);
-      tmem_st16(tlane + K + half * (K / 2) + ch * 16, lo);
-    }
-    {  // prefetch the next tile's slice: overlaps with the MMA wait and the epilogue below
-      const int tn = t + gridDim.x;
-      const int rown = tn * 128 + r;
-      if (tn < ntiles) {
-        const float* ar = A + (size_t)(rown < M ? rown : 0) * lda + half * (K / 2);
+      __syncthreads();
+      // thread = row view: my 32 of the 64 columns -> tf32 hi/lo -> TMEM
 #pragma unroll
-        for (int i = 0; i < K / 8; i++) pre[i] = *reinterpret_cast<const float4*>(ar + i * 4);
-      }
-    }
-    tc_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      uint32_t acc = 0;
-#pragma unroll
-      for (int term = 0; term < 3; term++) {
-        const uint32_t acol = term == 1 ? (uint32_t)K : 0u;
-        const uint32_t bsel = b_addr + (term == 2 ? (uint32_t)(N * K) * 4u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < K / 8; ks++) {
-          umma_ts(tbase + COL_D, tbase + acol + ks * 8, umma_desc(bsel + ks * 2 * LBO, LBO, 128u), IDESC, acc);
-          acc = 1;
-        }
-      }
-      umma_commit(mbar);
-    }
-    mbar_wait_(mbar, phase);
-    phase ^= 1;
-    tc_fence_after();
-#pragma unroll
-    for (int ch = 0; ch < N / 32; ch++) {
-      uint32_t v[16];
-      const int col = half * (N / 2) + ch * 16;
-      tmem_ld16(tlane + COL_D + col, v);
-      tc_wait_ld();
-      if (valid) {
-        float4* cp = reinterpret_cast<float4*>(C + (size_t)row * ldc + col);
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          float4 o = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                 __uint_as_float(v[4 * i + 3]));
+          const float4 x = *reinterpret_cast<const float4*>(stg + r * PITCH + half * 32 + ch * 16 + i * 4);
+          const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t h = tf32_hi_bits(xv[j]);
+            hi[4 * i + j] = h;
+            lo[4 * i + j] = __float_as_uint(xv[j] - __uint_as_float(h));
+          }
+        }
+        tmem_st16(tlane + half * 32 + ch * 16, hi);
+        tmem_st16(tlane + 64 + half * 32 + ch * 16, lo);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        uint32_t acc = kh == 0 ? 0u : 1u;
+#pragma unroll
+        for (int term = 0; term < 3; term++) {
+          const uint32_t acol = term == 1 ? 64u : 0u;
+          const uint32_t bsel = b_addr + (term == 2 ? (uint32_t)(N * K) * 4u : 0u) + (uint32_t)kh * 16u * LBO;
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) {
+            umma_ts(tbase + COL_D, tbase + acol + ks * 8, umma_desc(bsel + ks * 2 * LBO, LBO, 128u), IDESC, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(mbar);
+      }
+      mbar_wait_(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+    }
+    // epilogue in 64-column slabs: TMEM -> padded tile (thread = row) -> cooperative coalesced global store
+#pragma unroll 1
+    for (int nh = 0; nh < N / 64; nh++) {
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t v[16];
+        tmem_ld16(tlane + COL_D + nh * 64 + half * 32 + ch * 16, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          *reinterpret_cast<float4*>(stg + r * PITCH + half * 32 + ch * 16 + i * 4) =
+              make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                          __uint_as_float(v[4 * i + 3]));
+      }
+      tc_fence_before();
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int idx = tid + 256 * i;
+        const int rr = idx >> 4, c4 = idx & 15;
+        const int row = row0 + rr, col = nh * 64 + c4 * 4;
+        if (row < M) {
+          float4 o = *reinterpret_cast<const float4*>(stg + rr * PITCH + c4 * 4);
           if (bias) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + col + i * 4);
+            const float4 b = *reinterpret_cast<const float4*>(bias + col);
             o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
           }
           if (R) {
-            const float4 rr = *reinterpret_cast<const float4*>(R + (size_t)row * ldr + col + i * 4);
-            o.x += rr.x, o.y += rr.y, o.z += rr.z, o.w += rr.w;
+            const float4 x = *reinterpret_cast<const float4*>(R + (size_t)row * ldr + col);
+            o.x += x.x, o.y += x.y, o.z += x.z, o.w += x.w;
           }
+          float4* cp = reinterpret_cast<float4*>(C + (size_t)row * ldc + col);
           if (accum) {
-            const float4 c = cp[i];
+            const float4 c = *cp;
             o.x += c.x, o.y += c.y, o.z += c.z, o.w += c.w;
           }
-          cp[i] = o;
+          *cp = o;
         }
       }
+      __syncthreads();
     }
-    tc_fence_before();
-    __syncthreads();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(TCOLS));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
 }
 
 template <int K, int N>
 static void launch_gemm_tc_t(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M,
                              const float* bias, const float* R, int ldr, bool accum, int num_sms) {
-  constexpr size_t bytes = (size_t)(64 + 2 * N * K) * 4;
+  constexpr size_t bytes = (size_t)(64 + 2 * N * K + 128 * 68) * 4;
   static bool attr = false;
   if (!attr) {
     B2M_CK(cudaFuncSetAttribute(k_gemm_tc<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     attr = true;
   }
   const int ntiles = (M + 127) / 128;
-  const int per_sm = (2 * K + N <= 256) ? 2 : 1;
-  const int grid = std::min(ntiles, per_sm * num_sms);
+  const int grid = std::min(ntiles, 2 * num_sms);
   k_gemm_tc<K, N><<<grid, 256, bytes, st>>>(A, lda, Bcan, C, ldc, M, bias, R, ldr, accum ? 1 : 0);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
