@@ -96,6 +96,11 @@ __device__ __forceinline__ size_t tl4(int64_t tile, int r, int c) {
   return ((size_t)(tile * NC4 + (c >> 2)) * 128 + r);
 }
 
+// vectorised reduction: one L2 RED operation for 4 consecutive floats (sm_90+)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // instruction descriptors: c=F32, a=b=TF32, K-major, M=128
 constexpr uint32_t kIdescN64 = (1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24);
 constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | (16u << 17) | (8u << 24);
@@ -665,29 +670,31 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
           }
           __syncthreads();
           {
-            constexpr int RPP = 64 / (NTHR / 64);
-            const int c = tid & 63, part = tid >> 6;
-            const int col = br * 64 + c;
-            float sum = 0.f;
+            // 4 columns per thread so that every L2 reduction is a 16-byte vector RED
+            constexpr int RPP = 64 / (NTHR / 16);  // rows per reducing thread
+            const int c4 = tid & 15, part = tid >> 4;
+            const int col = br * 64 + c4 * 4;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             int cur = -1;
             const int rbeg = part * RPP;
             for (int rr = rbeg; rr < rbeg + RPP; rr++) {
               const int row = hp * 64 + rr;
               const int k = s_dst[row];
-              const float val = stage[rr * 65 + c];
+              const float v0 = stage[rr * 65 + c4 * 4], v1 = stage[rr * 65 + c4 * 4 + 1], v2 = stage[rr * 65 + c4 * 4 + 2],
+                          v3 = stage[rr * 65 + c4 * 4 + 3];
               if (k != cur) {
-                if (cur >= 0) atomicAdd(&a.gC[(size_t)cur * D2 + col], sum);
+                if (cur >= 0) red_add_v4(&a.gC[(size_t)cur * D2 + col], s0, s1, s2, s3);
                 cur = k;
-                sum = 0.f;
+                s0 = s1 = s2 = s3 = 0.f;
               }
               if (k >= 0) {
-                sum += val;
-                atomicAdd(&a.gA[(size_t)s_src[row] * D2 + col], val);
+                s0 += v0, s1 += v1, s2 += v2, s3 += v3;
+                red_add_v4(&a.gA[(size_t)s_src[row] * D2 + col], v0, v1, v2, v3);
                 const int bnd = s_bond[row];
-                if (useQ && bnd >= 0) a.gQ[(size_t)bnd * D2 + col] = val;
+                if (useQ && bnd >= 0) *reinterpret_cast<float4*>(&a.gQ[(size_t)bnd * D2 + col]) = make_float4(v0, v1, v2, v3);
               }
             }
-            if (cur >= 0) atomicAdd(&a.gC[(size_t)cur * D2 + col], sum);
+            if (cur >= 0) red_add_v4(&a.gC[(size_t)cur * D2 + col], s0, s1, s2, s3);
           }
           __syncthreads();
         }
