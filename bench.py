@@ -42,6 +42,20 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(natoms, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the edge-gather kernel, per launch, from the committed
+    `ncu --set full` capture of this same workload (profiles/r01_ncu_edge_gather.json); None for other workloads."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_edge_gather.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        if d.get("atoms") == natoms and world == 1:
+            return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -256,7 +270,8 @@ def run_ours(args):
         g_ms = float(np.mean(gather_ms))
         alg_bytes = SURVEY_BYTES_PER_EDGE * c["n_edges"]
         n_loc, n_own = c["n_own"] + c["n_halo"], c["n_own"]
-        own_bytes = 28.0 * c["n_edges"] + 512.0 * n_loc + 512.0 * n_own + 256.0 * n_own + 0.75 * 512.0 * c["n_bond_own"]
+        # own layout: indices+vec4 28 B, be 48 B, saved u|v 512 B per edge; A rows, C rows, agg, Q rows per node/bond
+        own_bytes = (28.0 + 48.0 + 512.0) * c["n_edges"] + 512.0 * n_loc + 512.0 * n_own + 256.0 * n_own + 0.75 * 512.0 * c["n_bond_own"]
         achieved = alg_bytes / (g_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
@@ -273,11 +288,11 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "atoms/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": natoms * (24 + 4) + 72 + 12, "d2h_bytes_per_step": natoms * 12 + 8 + 36 + natoms * 4},
-            "roofline": {"bound": "hbm", "kernel": "k_atomconv_fwd (edge gather)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k_atomconv_fwd_tc (edge gather, tcgen05)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "bytes_per_launch": alg_bytes, "bytes_convention": "SURVEY 8(d): 314 B/edge",
                          "kernel_ms": g_ms, "achieved_own_layout": own_bytes / (g_ms * 1e-3) / 1e9,
-                         "traffic": None},
+                         "traffic": ncu_traffic(natoms, world)},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = best_thread_count()

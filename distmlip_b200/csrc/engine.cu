@@ -416,7 +416,8 @@ static void gemm(b2m_engine* e, const float* A, int lda, const float* B, float* 
       return;
     }
   }
-  gemm(e, A, lda, B, C, ldc, M, N, K, bias, R, ldr, accum);
+  B2M_REQUIRE(!e->use_tc, B2M_ERR_STATE, "tcgen05 path: GEMM operand without a canonical copy");
+  launch_gemm(e->st, A, lda, B, C, ldc, M, N, K, bias, R, ldr, accum);  // FP32-FFMA tile kernel (legacy path only)
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1226,33 +1226,35 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
         }
         gbar(g);
         {
-          const int c = gt & 63, part = gt >> 6;
-          const int col = br * 64 + c;
-          float sb = 0.f, sc = 0.f;
+          // 4 columns per thread: every reduction below is a 16-byte vector RED
+          const int c4 = gt & 15, part = gt >> 4;  // 16 parts x 4 rows
+          const int col = br * 64 + c4 * 4;
+          float sb0 = 0.f, sb1 = 0.f, sb2 = 0.f, sb3 = 0.f, sc0 = 0.f, sc1 = 0.f, sc2 = 0.f, sc3 = 0.f;
           int curb = -1, curc = -1;
-          const int rbeg = part * 16;
-          for (int rr = rbeg; rr < rbeg + 16; rr++) {
+          const int rbeg = part * 4;
+          for (int rr = rbeg; rr < rbeg + 4; rr++) {
             const int rowi = hp * 64 + rr;
             const int kb = s_b[rowi], kc = s_c[rowi];
-            const float val = stage[rr * 65 + c];
+            const float v0 = stage[rr * 65 + c4 * 4], v1 = stage[rr * 65 + c4 * 4 + 1], v2 = stage[rr * 65 + c4 * 4 + 2],
+                        v3 = stage[rr * 65 + c4 * 4 + 3];
             if (kb != curb) {
-              if (curb >= 0) atomicAdd(&a.gHb[(size_t)curb * D2 + col], sb);
+              if (curb >= 0) red_add_v4(&a.gHb[(size_t)curb * D2 + col], sb0, sb1, sb2, sb3);
               curb = kb;
-              sb = 0.f;
+              sb0 = sb1 = sb2 = sb3 = 0.f;
             }
             if (kc != curc) {
-              if (curc >= 0) atomicAdd(&a.gXc[(size_t)curc * D2 + col], sc);
+              if (curc >= 0) red_add_v4(&a.gXc[(size_t)curc * D2 + col], sc0, sc1, sc2, sc3);
               curc = kc;
-              sc = 0.f;
+              sc0 = sc1 = sc2 = sc3 = 0.f;
             }
             if (kb >= 0) {
-              sb += val;
-              sc += val;
-              atomicAdd(&a.gHa[(size_t)s_a[rowi] * D2 + col], val);
+              sb0 += v0, sb1 += v1, sb2 += v2, sb3 += v3;
+              sc0 += v0, sc1 += v1, sc2 += v2, sc3 += v3;
+              red_add_v4(&a.gHa[(size_t)s_a[rowi] * D2 + col], v0, v1, v2, v3);
             }
           }
-          if (curb >= 0) atomicAdd(&a.gHb[(size_t)curb * D2 + col], sb);
-          if (curc >= 0) atomicAdd(&a.gXc[(size_t)curc * D2 + col], sc);
+          if (curb >= 0) red_add_v4(&a.gHb[(size_t)curb * D2 + col], sb0, sb1, sb2, sb3);
+          if (curc >= 0) red_add_v4(&a.gXc[(size_t)curc * D2 + col], sc0, sc1, sc2, sc3);
         }
         gbar(g);
       }
