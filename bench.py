@@ -152,7 +152,7 @@ def best_thread_count():
     """PyTorch CPU ops on these small tensors get slower past a few dozen threads; pick the fastest of a
     few thread counts on a 512-atom probe (config[0]) so the CPU arm is not handicapped on many-core hosts."""
     cores = os.cpu_count() or 1
-    cands = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores})
+    cands = sorted({c for c in (8, 16, 32) if c <= cores}) or [cores]
     best, best_t = cands[0], 1e30
     for c in cands:
         cpu_reference_step(4, c)
