@@ -10,8 +10,8 @@ from oracle import manual_ref as M
 from oracle.chgnet_ref import CHGNetRef, build_line_graph, potential_ref
 
 
-def make_model(seed=0, scale=1.0):
-    m = CHGNetRef(seed=seed)
+def make_model(seed=0, scale=1.0, num_blocks=4):
+    m = CHGNetRef(seed=seed, num_blocks=num_blocks)
     if scale != 1.0:
         with torch.no_grad():
             for n, p in m.named_parameters():

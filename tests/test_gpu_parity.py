@@ -311,3 +311,29 @@ def test_tcgen05_and_ffma_paths_agree(model):
     assert abs(E1 - E2) / len(atoms) < 1e-7 and np.abs(F1 - F2).max() < 1e-6 and np.abs(S1 - S2).max() < 1e-6
     e_ffma.close()
     e_tc.close()
+
+
+@pytest.mark.parametrize("nb", [2, 3])
+def test_other_block_counts(nb):
+    """n_blocks is read from the model (chgnet.py:298): the layer loops, the dead last angle update and the
+    saved-tensor bookkeeping must hold for depths other than the default 4."""
+    m = make_model(seed=5, num_blocks=nb)
+    e = engine_from_model(m)
+    atoms = si_diamond(3, seed=29)
+    E, F, S = run_engine(e, m, atoms)
+    Eo, Fo, So, _ = potential_ref(make_model(seed=5, num_blocks=nb).double(), atoms, dtype=torch.float64)
+    assert abs(E - Eo.item()) / len(atoms) < TOL_E and np.abs(F - Fo.numpy()).max() < TOL_F
+    assert np.abs(S - So.numpy()).max() < TOL_S
+    e.close()
+
+
+def test_empty_and_degenerate_inputs(eng, model):
+    from distmlip_b200._lib import B2MError
+
+    with pytest.raises(B2MError):
+        eng.set_structure(np.zeros((0, 3)), np.eye(3) * 10, np.zeros(0, dtype=np.int32), np.ones(3, dtype=np.int32))
+    with pytest.raises(B2MError) as ei:
+        eng.set_structure(np.zeros((2, 3)) + [[0, 0, 0], [1, 1, 1]], np.zeros((3, 3)), np.zeros(2, dtype=np.int32),
+                          np.ones(3, dtype=np.int32))
+    assert "singular" in str(ei.value)
+    check_vs_oracle(eng, model, si_diamond(2))  # handle still usable
