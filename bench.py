@@ -28,7 +28,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("B2M_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (no NCCL banner)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL banner -> stderr)
 
 METRIC = "atoms/sec (energy+forces) CHGNet a-Si r_cut=5A"
 SURVEY_BYTES_PER_EDGE = 314.0  # SURVEY.md 8(d), rbf-recompute variant, D=64 fp32
