@@ -711,14 +711,16 @@ static void backward(b2m_engine* e) {
   for (int l = nb - 2; l >= 0; l--) {
     const BondLayerW& w = e->bw[l];
     if (l < nb - 2) {
-      line_projections(e, l, false);
+      // the tcgen05 backward works from the tensors saved by the forward; only the FFMA generation recomputes
+      // the first-layer projections
+      if (!e->use_tc) line_projections(e, l, false);
       LineArgs a = line_args(e, l, false);
       line_bwd_common(e, l, false, a);
       halo_backward(e, e->gh.p, true);
     }
     launch_bond_update_bwd(e->st, g.B_own, g.b_vec.p, e->rp3, e->d_W3bw, e->gh.p, e->upd[l].p, e->gupd.p, e->gdb.p);
     gemm(e, e->gupd.p, D, w.Wout_raw, e->gaggB.p, D, g.B_own, D, D, nullptr, nullptr, 0, false);
-    line_projections(e, l, true);
+    if (!e->use_tc) line_projections(e, l, true);
     LineArgs a = line_args(e, l, true);
     a.gaggB = e->gaggB.p;
     line_bwd_common(e, l, true, a);
