@@ -206,12 +206,12 @@ def run_ours(args):
 
     from distmlip_b200.implementations.matgl import CHGNet_Dist, Potential_Dist
     from distmlip_b200.structures import si_diamond
-    from tests._util import make_model  # random-init weights of the CHGNet architecture (seed 0)
+    from distmlip_b200.random_init import RandomCHGNet  # seeded random-init weights of the CHGNet architecture
 
     n = args.cells
     atoms = si_diamond(n, nz=n * world)
     natoms = len(atoms)
-    model = CHGNet_Dist.from_existing(make_model())
+    model = CHGNet_Dist.from_existing(RandomCHGNet(seed=0))
     model.enable_distributed_mode(list(range(world)) if world > 1 else [local])
     pot = Potential_Dist(model=model, calc_forces=True, calc_stresses=True)
     eng = model._engine

@@ -82,3 +82,39 @@ def test_from_existing_and_cpu_partitions_rejected():
     assert m.dist_enabled is False and float(m.cutoff) == 5.0 and m.n_blocks == 4
     with pytest.raises(RuntimeError):
         m.enable_distributed_mode(["cpu", "cpu"])
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under distmlip_b200/ may import it, and bench.py only inside its
+    CPU-baseline / reference-arm functions."""
+    import ast
+
+    pkg = os.path.join(ROOT, "distmlip_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                for node in ast.walk(ast.parse(src)):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom):
+                        names = [node.module or ""]
+                    assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (f, names)
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n) for n in ast.walk(fn))
+        if uses:
+            assert fn.name in ("cpu_reference_step",), fn.name
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any("oracle" in ast.dump(n) for n in top)
+
+
+def test_random_init_container_is_accepted():
+    from distmlip_b200.implementations.matgl import CHGNet_Dist
+    from distmlip_b200.random_init import RandomCHGNet
+    from tests._util import make_model
+
+    m = CHGNet_Dist.from_existing(RandomCHGNet(seed=1))
+    ref = make_model().state_dict()
+    assert set(m._state_dict) == set(ref) and all(m._state_dict[k].shape == ref[k].shape for k in ref)
