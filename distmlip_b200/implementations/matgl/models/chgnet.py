@@ -109,6 +109,10 @@ class CHGNet_Dist:
     def _species_of(self, atoms):
         """element index per atom (chgnet.py:66-72), vectorised through atomic numbers when the Atoms object has them"""
         if hasattr(atoms, "get_atomic_numbers"):
+            z = np.asarray(atoms.numbers) if hasattr(atoms, "numbers") else np.asarray(atoms.get_atomic_numbers())
+            cached = self.__dict__.get("_species_cache")
+            if cached is not None and cached[0].shape == z.shape and np.array_equal(cached[0], z):
+                return cached[1]  # MD / relaxation: the composition does not change between calls
             lut = self.__dict__.get("_z_lut")
             if lut is None:
                 from distmlip_b200.structures import Z_OF
@@ -118,9 +122,10 @@ class CHGNet_Dist:
                     if el in Z_OF:
                         lut[Z_OF[el]] = idx
                 self._z_lut = lut
-            sp = lut[np.asarray(atoms.get_atomic_numbers())]
+            sp = lut[z]
             if (sp < 0).any():
                 raise KeyError("structure contains an element that is not in model.element_types")
+            self._species_cache = (z.copy(), sp)
             return sp
         return np.array([self.element_to_index[s] for s in atoms.get_chemical_symbols()], dtype=np.int32)
 

@@ -55,7 +55,9 @@ class Potential_Dist:
         # kept for signature compatibility; the graph build has no host threads
         _ = self.num_threads if self.num_threads else int(os.environ.get("DISTMLIP_NUM_THREADS", 8))
         lattice_matrix = np.array(atoms.get_cell())
-        cart_coords = np.asarray(atoms.get_positions(wrap=False))  # ASE already returns a copy
+        # `atoms.positions` is ASE's internal array (no copy); it is copied once into the engine's pinned staging buffer
+        cart_coords = np.asarray(getattr(atoms, "positions", None) if hasattr(atoms, "positions")
+                                 else atoms.get_positions(wrap=False))
         pbc = atoms.get_pbc().astype(np.int64)
         model = self.model
         species = model._species_of(atoms)

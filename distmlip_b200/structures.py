@@ -70,6 +70,16 @@ class SimpleAtoms:
     def get_chemical_symbols(self):
         return list(self._symbols)
 
+    @property
+    def positions(self):  # ase.Atoms.positions: the internal array, no copy
+        return self._positions
+
+    @property
+    def numbers(self):  # ase.Atoms.numbers
+        if getattr(self, "_numbers", None) is None:
+            self._numbers = np.array([Z_OF[s] for s in self._symbols], dtype=np.int64)
+        return self._numbers
+
     def get_atomic_numbers(self):
         if getattr(self, "_numbers", None) is None:
             self._numbers = np.array([Z_OF[s] for s in self._symbols], dtype=np.int64)
