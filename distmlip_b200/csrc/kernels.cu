@@ -1048,6 +1048,7 @@ __global__ void __launch_bounds__(256) k_bond_node(int nb, const float4* __restr
                                                    float* __restrict__ gdb) {
   __shared__ float be_s[32][12], dbe_s[32][12], gk_s[32][12];
   __shared__ float Ws[64 * 9];
+  __shared__ float P[32][65];  // MODE 1: gh*upd, MODE 2: gh0 (staged once, coalesced)
   const int b0 = blockIdx.x * 32, tid = threadIdx.x;
   for (int i = tid; i < 576; i += 256) Ws[i] = W[i];
   for (int i = tid; i < 32 * 9; i += 256) {
@@ -1058,33 +1059,37 @@ __global__ void __launch_bounds__(256) k_bond_node(int nb, const float4* __restr
     dbe_s[r][k] = dbe;
   }
   __syncthreads();
-  if (MODE == 0 || MODE == 1) {
-    for (int i = tid; i < 32 * 64; i += 256) {
-      const int r = i >> 6, c = i & 63;
-      if (b0 + r >= nb) continue;
-      float w = 0.f;
-#pragma unroll
-      for (int k = 0; k < 9; k++) w = fmaf(be_s[r][k], Ws[c * 9 + k], w);
+  for (int i = tid; i < 32 * 64; i += 256) {
+    const int r = i >> 6, c = i & 63;
+    float pv = 0.f;
+    if (b0 + r < nb) {
       const size_t o = (size_t)(b0 + r) * 64 + c;
-      if (MODE == 0)
-        out[o] = x0[o] + x1[o] * w;
-      else
-        out[o] = x0[o] * w;
+      const float a0 = x0[o];
+      if (MODE == 2) {
+        pv = a0;
+      } else {
+        float w = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; k++) w = fmaf(be_s[r][k], Ws[c * 9 + k], w);
+        const float a1 = x1[o];
+        if (MODE == 0) {
+          out[o] = a0 + a1 * w;
+        } else {
+          out[o] = a0 * w;
+          pv = a0 * a1;
+        }
+      }
     }
+    if (MODE != 0) P[r][c] = pv;
   }
   if (MODE == 1 || MODE == 2) {
-    // gk[r][k] = sum_c g[r][c] * (MODE1: upd[r][c]) * W[c][k];  gdb[r] += sum_k gk dbe_k
+    __syncthreads();
+    // gk[r][k] = sum_c P[r][c] W[c][k];  gdb[r] += sum_k gk dbe_k
     for (int i = tid; i < 32 * 9; i += 256) {
       const int r = i / 9, k = i % 9;
       float s = 0.f;
-      if (b0 + r < nb) {
-        const size_t o = (size_t)(b0 + r) * 64;
-        for (int c = 0; c < 64; c++) {
-          float g = x0[o + c];
-          if (MODE == 1) g *= x1[o + c];
-          s = fmaf(g, Ws[c * 9 + k], s);
-        }
-      }
+#pragma unroll 8
+      for (int c = 0; c < 64; c++) s = fmaf(P[r][c], Ws[c * 9 + k], s);
       gk_s[r][k] = s * dbe_s[r][k];
     }
     __syncthreads();
@@ -1125,17 +1130,20 @@ __global__ void __launch_bounds__(256) k_angle_init_bwd(int64_t na, const int* _
                                                         float* __restrict__ gbvec) {
   __shared__ float gf_s[32][12];
   __shared__ float Ws[64 * 9];
+  __shared__ float G[32][65];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const int tid = threadIdx.x;
   for (int i = tid; i < 576; i += 256) Ws[i] = Wae[i];
+  for (int i = tid; i < 32 * 64; i += 256) {
+    const int r = i >> 6, c = i & 63;
+    G[r][c] = (r0 + r < na) ? gang0[(size_t)(r0 + r) * 64 + c] : 0.f;
+  }
   __syncthreads();
   for (int i = tid; i < 32 * 9; i += 256) {
     const int r = i / 9, k = i % 9;
     float s = 0.f;
-    if (r0 + r < na) {
-      const float* g = gang0 + (size_t)(r0 + r) * 64;
-      for (int c = 0; c < 64; c++) s = fmaf(g[c], Ws[c * 9 + k], s);
-    }
+#pragma unroll 8
+    for (int c = 0; c < 64; c++) s = fmaf(G[r][c], Ws[c * 9 + k], s);
     gf_s[r][k] = s;
   }
   __syncthreads();
