@@ -68,31 +68,44 @@ class ClockSampler:
         self.rows = []
         self.proc = None
 
-    def start(self):
+    def start(self, wait_first=5.0):
+        """Launch the poller and wait for its first row: NVML start-up (up to a second on a fresh box) must not eat
+        the timed region, which is only a few hundred milliseconds long."""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                  str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < wait_first:
+                time.sleep(0.01)
         except Exception:  # noqa: BLE001
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def stop(self, windows):
+        """windows: [(label, t_begin, t_end)] in perf_counter time; rows of the first window are used, the later ones
+        (also under load) only if the first caught fewer than two samples."""
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
             self.proc.kill()
+        used, rows = [], []
+        for label, tb, te in windows:
+            rows += [r[1:] for r in self.rows if tb <= r[0] <= te]
+            used.append(label)
+            if len(rows) >= 2:
+                break
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
@@ -102,7 +115,7 @@ class ClockSampler:
             except Exception:  # noqa: BLE001
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": "+".join(used)}
 
 
 def cpu_reference_step(n_cells, threads):
@@ -225,11 +238,11 @@ def run_ours(args):
     # ---- resident-graph throughput (`value`) ----
     out = pot(atoms)  # builds graph + first compute
     sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         eng.compute_resident(1)
     barrier()
-    if rank == 0:
-        sampler.start()
     t0 = time.perf_counter()
     dev_ms, gather_ms, launches = 0.0, [], 0
     for _ in range(args.steps):
@@ -238,8 +251,8 @@ def run_ours(args):
         gather_ms.append(eng.timings()["edge_gather_ms"])
         launches += eng.counts()["launches"]
     barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
+    t1 = time.perf_counter()
+    wall_ms = (t1 - t0) * 1e3
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -251,12 +264,14 @@ def run_ours(args):
     for _ in range(max(1, min(args.warmup, 2))):
         pot(atoms)
     barrier()
-    t0 = time.perf_counter()
+    t2b = time.perf_counter()
     for _ in range(args.steps):
         out = pot(atoms)
         _ = float(out[0].item()) + float(out[1][0, 0])
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t2e = time.perf_counter()
+    e2e_ms = (t2e - t2b) * 1e3 / args.steps
+    clocks = sampler.stop([("timed", t0, t1), ("e2e", t2b, t2e)]) if rank == 0 else None
     t2 = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)

@@ -10,7 +10,13 @@ long long g_launch_count = 0;
 // ============================================================================================
 // device helpers
 // ============================================================================================
-__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// MUFU.EX2 + MUFU.RCP, flush-to-zero forms (same bits as __fdividef/__expf for normal results, no range fix-ups)
+__device__ __forceinline__ float sigm(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 __device__ __forceinline__ float silu_f(float x) { return x * sigm(x); }
 __device__ __forceinline__ float dsilu_f(float x) {
   float s = sigm(x);

@@ -148,6 +148,7 @@ struct AtomConvTcW {
   const float* W2can;   // [4][4096]: W2L hi, W2L lo, W2G hi, W2G lo   (N=64, K=64)
   const float* Mcan;    // [2][2048]: M hi, M lo                        (N=128, K=16; k>=9 zero)
   const float* W2Tcan;  // [4][4096]: W2L^T hi, lo, W2G^T hi, lo        (backward: ghid = g . W2)
+  int l2pf = 0;         // set by the launcher: prefetch the next tile's streamed blocks into L2
 };
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
@@ -160,6 +161,7 @@ struct LineTcW {
   const float* W2can;   // [4][4096]: second layers (HIDDEN)
   const float* W2Tcan;  // [4][4096]: transposed second layers (HIDDEN, backward)
   const float* WgTcan;  // [4][4096]: per branch (N=64 angle cols, K=64 first-layer cols): L hi, L lo, G hi, G lo
+  int l2pf = 0;         // set by the launcher: prefetch the next tile's streamed blocks into L2
 };
 void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms);
 void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms);

@@ -12,7 +12,15 @@
 
 namespace b2m {
 
-__device__ __forceinline__ float sigm_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// sigmoid on MUFU.EX2 + MUFU.RCP with flush-to-zero: the same bits as __fdividef(1, 1 + __expf(-x)) wherever the result
+// is a normal number (|x| < 87), without the three range fix-up instructions (FSETP + 2 predicated FMUL) the non-ftz
+// forms carry -- activations are 35-45 % of the instructions of the fused tile kernels (profiles/r01_stalls_*.txt).
+__device__ __forceinline__ float sigm_(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 __device__ __forceinline__ float silu_(float x) { return x * sigm_(x); }
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -101,6 +109,56 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Streaming operands of the NEXT tile of a persistent CTA (saved u|v, silu', radial basis, index blocks: contiguous
+// per tile in the tile-interleaved layouts) are pulled into L2 while the current tile computes: with two tiles in
+// flight per SM there is not enough parallelism to hide a DRAM round trip behind other warps.  Pure hint.
+__device__ __forceinline__ void l2_prefetch(const void* base, int bytes, int tid, int nthr) {
+  const char* p = reinterpret_cast<const char*>(base);
+  for (int o = tid * 128; o < bytes; o += nthr * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+
+// packed fp32 FMA (FFMA2): (d0, d1) += a * (b0, b1), each half an IEEE fma -- same bits as two fmaf, one issue slot
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+  uint64_t A, B, C, D;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a), "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(C));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+}
+// w[0..15] = sum_k b[k] * WT[k][col0 .. col0+15]   (WT: [9][64] k-major in shared memory, col0 % 16 == 0)
+__device__ __forceinline__ void radial_dot16(const float* WT, int col0, const float (&b)[9], float (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) w[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+#pragma unroll
+    for (int c4 = 0; c4 < 4; c4++) {
+      const float4 x = *reinterpret_cast<const float4*>(WT + k * 64 + col0 + c4 * 4);
+      ffma2(w[4 * c4], w[4 * c4 + 1], b[k], x.x, x.y);
+      ffma2(w[4 * c4 + 2], w[4 * c4 + 3], b[k], x.z, x.w);
+    }
+  }
+}
+
+__device__ __forceinline__ void radial_dot4(const float* WT, int col0, const float (&b)[9], float (&w)[4]) {
+  w[0] = w[1] = w[2] = w[3] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const float4 x = *reinterpret_cast<const float4*>(WT + k * 64 + col0);
+    ffma2(w[0], w[1], b[k], x.x, x.y);
+    ffma2(w[2], w[3], b[k], x.z, x.w);
+  }
+}
+
+static int l2pf_enabled() {  // B2M_L2_PREFETCH=0 switches the hints off (A/B measurements)
+  static const int v = [] {
+    const char* e = getenv("B2M_L2_PREFETCH");
+    return e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }();
+  return v;
+}
+
 // instruction descriptors: c=F32, a=b=TF32, K-major, M=128
 constexpr uint32_t kIdescN64 = (1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24);
 constexpr uint32_t kIdescN128 = (1u << 4) | (2u << 7) | (2u << 10) | (16u << 17) | (8u << 24);
@@ -165,7 +223,10 @@ struct FwdTcSmem {
 
 // NTHR = 256: two threads per row (32 columns of each branch per thread, <=128 registers);
 // NTHR = 512: four threads per row (16 columns, <=64 registers) -> twice the resident warps for the same TMEM/smem.
-template <int NTHR>
+// PF = true: the gathers of A[src] / C[dst] for the next 16-column block are issued one block ahead (the first
+// block before the wait for GEMM1), so their L2 latency overlaps the tensor-core wait and the activation math of
+// the current block instead of following it (the gather wait was 16 % of the samples: profiles/r01_stalls_*.txt).
+template <int NTHR, bool PF>
 __global__ void __launch_bounds__(NTHR, 2) k_atomconv_fwd_tc(const AtomConvArgs a, const AtomConvTcW w) {
   constexpr int NP = NTHR / 128;   // threads per row
   constexpr int CPT = 64 / NP;     // columns of each branch per thread
@@ -176,10 +237,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_fwd_tc(const AtomConvArgs 
   float* W2s = smem + FwdTcSmem::kW2;
   float* Ms = smem + FwdTcSmem::kM;
   float* msg = smem + FwdTcSmem::kMsg;
-  float* be_s = smem + FwdTcSmem::kBe;
   float* wabW = smem + FwdTcSmem::kWab;
   float* b2s = smem + FwdTcSmem::kB2;
-  float* s_d = smem + FwdTcSmem::kD;
   int* s_src = reinterpret_cast<int*>(smem + FwdTcSmem::kIdx);
   int* s_dst = s_src + 128;
   int* s_bond = s_dst + 128;
@@ -203,7 +262,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_fwd_tc(const AtomConvArgs 
   }
   for (int i = tid; i < 4 * 1024; i += NTHR) reinterpret_cast<float4*>(W2s)[i] = reinterpret_cast<const float4*>(w.W2can)[i];
   for (int i = tid; i < 2 * 512; i += NTHR) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
-  for (int i = tid; i < 576; i += NTHR) wabW[i] = a.Wabw[i];
+  for (int i = tid; i < 576; i += NTHR) wabW[(i % 9) * 64 + i / 9] = a.Wabw[i];  // k-major [9][64]
   if (tid < 128) b2s[tid] = a.b2[tid];
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
@@ -221,18 +280,26 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_fwd_tc(const AtomConvArgs 
     const int nvalid = (int)min((int64_t)128, a.E - e0);
     if (tid < 128) {
       int src = 0, dst = -1, bond = -1;
-      float d = 1.f;
       if (tid < nvalid) {
         const int64_t e = e0 + tid;
         src = a.e_src[e];
         dst = a.e_dst[e];
         bond = a.e_bond[e];
-        d = a.e_vec[e].w;
       }
       s_src[tid] = src;
       s_dst[tid] = dst;
       s_bond[tid] = bond;
-      s_d[tid] = d;
+    }
+    if (w.l2pf) {
+      const int64_t tn = t + gridDim.x;
+      if (tn < ntiles) {
+        l2_prefetch(a.be + tn * (128 * 12), 128 * 12 * 4, tid, NTHR);
+        if (tn * 128 + 128 <= a.E && tid >= 128 && tid < 140) {
+          const int which = (tid - 128) >> 2, line = (tid - 128) & 3;
+          const int* base = which == 0 ? a.e_src : which == 1 ? a.e_dst : a.e_bond;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + tn * 128 + line * 32));
+        }
+      }
     }
     __syncthreads();
     float bek[9];  // radial basis of my row (precomputed once per step: launch_edge_basis)
@@ -283,6 +350,14 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_fwd_tc(const AtomConvArgs 
     const float* Crow = a.Cproj + (size_t)(valid ? dst : 0) * D2;
     const float* Qrow = viaQ ? a.Qproj + (size_t)bond * D2 : nullptr;
     // ---- first layer epilogue + second layer, branch by branch (0: "layers", 1: "gates") ----
+    float4 pa[4], pc[4];  // PF: gathered rows of the next 16-column block
+    if (PF) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        pa[i] = *reinterpret_cast<const float4*>(Arow + c0 + i * 4);
+        pc[i] = *reinterpret_cast<const float4*>(Crow + c0 + i * 4);
+      }
+    }
 #pragma unroll 1
     for (int br = 0; br < 2; br++) {
       mbar_wait_(&mbar[br], phase);
@@ -294,12 +369,29 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_fwd_tc(const AtomConvArgs 
         tmem_ld16(tlane + COL_D + cb + ch * 16, v);
         tc_wait_ld();
         float av[16], cv[16];
+        if (PF) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float4 x = *reinterpret_cast<const float4*>(Arow + cb + ch * 16 + i * 4);
-          const float4 y = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
-          av[4 * i] = x.x, av[4 * i + 1] = x.y, av[4 * i + 2] = x.z, av[4 * i + 3] = x.w;
-          cv[4 * i] = y.x, cv[4 * i + 1] = y.y, cv[4 * i + 2] = y.z, cv[4 * i + 3] = y.w;
+          for (int i = 0; i < 4; i++) {
+            av[4 * i] = pa[i].x, av[4 * i + 1] = pa[i].y, av[4 * i + 2] = pa[i].z, av[4 * i + 3] = pa[i].w;
+            cv[4 * i] = pc[i].x, cv[4 * i + 1] = pc[i].y, cv[4 * i + 2] = pc[i].z, cv[4 * i + 3] = pc[i].w;
+          }
+          // next block: (br, ch + 1), or the first block of the other branch
+          const int nb = ch + 1 < NCH ? cb + (ch + 1) * 16 : 64 + c0;
+          if (ch + 1 < NCH || br == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              pa[i] = *reinterpret_cast<const float4*>(Arow + nb + i * 4);
+              pc[i] = *reinterpret_cast<const float4*>(Crow + nb + i * 4);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float4 x = *reinterpret_cast<const float4*>(Arow + cb + ch * 16 + i * 4);
+            const float4 y = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
+            av[4 * i] = x.x, av[4 * i + 1] = x.y, av[4 * i + 2] = x.z, av[4 * i + 3] = x.w;
+            cv[4 * i] = y.x, cv[4 * i + 1] = y.y, cv[4 * i + 2] = y.z, cv[4 * i + 3] = y.w;
+          }
         }
         if (viaQ) {
 #pragma unroll
@@ -351,6 +443,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_fwd_tc(const AtomConvArgs 
         uint32_t u[16], g[16];
         tmem_ld16(tlane + COL_D + c0 + ch * 16, u);
         tmem_ld16(tlane + COL_D + 64 + c0 + ch * 16, g);
+        float wab[16];  // shared bond weights w_ab = be . Wabw^T for my 16 columns (packed FMAs while the TMEM loads fly)
+        radial_dot16(wabW, c0 + ch * 16, bek, wab);
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; i++) {
@@ -360,10 +454,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_fwd_tc(const AtomConvArgs 
           g[i] = __float_as_uint(vv);
           const float oL = silu_(uu);
           const float oG = sigm_(vv);
-          float wab = 0.f;
-#pragma unroll
-          for (int k = 0; k < 9; k++) wab = fmaf(bek[k], wabW[c * 9 + k], wab);
-          mv[ch * 16 + i] = valid ? oL * oG * wab : 0.f;
+          mv[ch * 16 + i] = valid ? oL * oG * wab[i] : 0.f;
         }
         if (a.uv_save != nullptr && valid) {
           float4* puv = reinterpret_cast<float4*>(a.uv_save);
@@ -423,16 +514,14 @@ struct BwdTcSmem {
   static constexpr int kW2T = 64;                  // 4 x 4096
   static constexpr int kM = kW2T + 4 * 4096;       // 2 x 2048 (canonical)
   static constexpr int kStage = kM + 2 * 2048;     // [64][65]
-  static constexpr int kBe = kStage + 64 * 65;     // [128][9]
-  static constexpr int kDbe = kBe + 128 * 9;       // [128][9]
-  static constexpr int kWab = kDbe + 128 * 9;      // 576
-  static constexpr int kD = kWab + 576;            // [128]
-  static constexpr int kIdx = kD + 128;            // 3 x 128 ints
+  static constexpr int kMrow = kStage + 64 * 65;   // [128][12] row-major copy of M (k >= 9 zero)
+  static constexpr int kWab = kMrow + 128 * 12;    // 576, k-major [9][64]
+  static constexpr int kIdx = kWab + 576;          // 3 x 128 ints
   static constexpr int kTotal = kIdx + 3 * 128;
   static constexpr size_t bytes = (size_t)kTotal * 4;
 };
 
-template <int NTHR>
+template <int NTHR, bool PF>  // PF: gathers of A[src] / C[dst] one 16-column block ahead (see the forward)
 __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs a, const AtomConvTcW w) {
   constexpr int NP = NTHR / 128;   // threads per row
   constexpr int CPT = 64 / NP;     // columns of each branch per thread
@@ -443,10 +532,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
   float* W2Ts = smem + BwdTcSmem::kW2T;
   float* Ms = smem + BwdTcSmem::kM;
   float* stage = smem + BwdTcSmem::kStage;
-  float* be_s = smem + BwdTcSmem::kBe;
-  float* dbe_s = smem + BwdTcSmem::kDbe;
+  float* Mrow = smem + BwdTcSmem::kMrow;  // M [128][12] in plain row-major fp32 (dE/dbe contraction)
   float* wabW = smem + BwdTcSmem::kWab;
-  float* s_d = smem + BwdTcSmem::kD;
   int* s_src = reinterpret_cast<int*>(smem + BwdTcSmem::kIdx);
   int* s_dst = s_src + 128;
   int* s_bond = s_dst + 128;
@@ -470,7 +557,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
   }
   for (int i = tid; i < 4 * 1024; i += NTHR) reinterpret_cast<float4*>(W2Ts)[i] = reinterpret_cast<const float4*>(w.W2Tcan)[i];
   for (int i = tid; i < 2 * 512; i += NTHR) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
-  for (int i = tid; i < 576; i += NTHR) wabW[i] = a.Wabw[i];
+  for (int i = tid; i < 576; i += NTHR) wabW[(i % 9) * 64 + i / 9] = a.Wabw[i];
+  for (int i = tid; i < 128 * 12; i += NTHR) Mrow[i] = (i % 12) < 9 ? a.M[(i / 12) * 9 + i % 12] : 0.f;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -487,18 +575,28 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
     const int nvalid = (int)min((int64_t)128, a.E - e0);
     if (tid < 128) {
       int src = 0, dst = -1, bond = -1;
-      float d = 1.f;
       if (tid < nvalid) {
         const int64_t e = e0 + tid;
         src = a.e_src[e];
         dst = a.e_dst[e];
         bond = a.e_bond[e];
-        d = a.e_vec[e].w;
       }
       s_src[tid] = src;
       s_dst[tid] = dst;
       s_bond[tid] = bond;
-      s_d[tid] = d;
+    }
+    if (w.l2pf) {
+      const int64_t tn = t + gridDim.x;
+      if (tn < ntiles) {
+        l2_prefetch(a.uv + tn * (128 * 128), 128 * 128 * 4, tid, NTHR);
+        l2_prefetch(a.be + tn * (128 * 12), 128 * 12 * 4, tid, NTHR);
+        l2_prefetch(a.dbe + tn * (128 * 12), 128 * 12 * 4, tid, NTHR);
+        if (tn * 128 + 128 <= a.E && tid >= 128 && tid < 140) {
+          const int which = (tid - 128) >> 2, line = (tid - 128) & 3;
+          const int* base = which == 0 ? a.e_src : which == 1 ? a.e_dst : a.e_bond;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + tn * 128 + line * 32));
+        }
+      }
     }
     __syncthreads();
     float bek[9], dbek[9];
@@ -555,10 +653,18 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
     const float4* uv4 = reinterpret_cast<const float4*>(a.uv);
     const float* gmrow = a.gagg + (size_t)(valid ? dst : 0) * D;
     float gdpart = 0.f;   // dE/dd_e contribution of this thread's columns
-    float gbeM[9];
+    float gbeM[12];  // k >= 9 stay zero (padding of the packed FMAs)
 #pragma unroll
-    for (int k = 0; k < 9; k++) gbeM[k] = 0.f;
+    for (int k = 0; k < 12; k++) gbeM[k] = 0.f;
 
+    float4 pa[4], pc[4];
+    if (PF) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        pa[i] = *reinterpret_cast<const float4*>(Arow + c0 + i * 4);
+        pc[i] = *reinterpret_cast<const float4*>(Crow + c0 + i * 4);
+      }
+    }
 #pragma unroll 1
     for (int br = 0; br < 2; br++) {
       mbar_wait_(&mbar[br], phase);
@@ -570,10 +676,29 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
         uint32_t v[16], hi[16], lo[16];
         tmem_ld16(tlane + COL_D + cb + ch * 16, v);
         tc_wait_ld();
+        float4 xa[4], yc[4];
+        if (PF) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) xa[i] = pa[i], yc[i] = pc[i];
+          const int nb = ch + 1 < NCH ? cb + (ch + 1) * 16 : 64 + c0;
+          if (ch + 1 < NCH || br == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              pa[i] = *reinterpret_cast<const float4*>(Arow + nb + i * 4);
+              pc[i] = *reinterpret_cast<const float4*>(Crow + nb + i * 4);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            xa[i] = *reinterpret_cast<const float4*>(Arow + cb + ch * 16 + i * 4);
+            yc[i] = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          const float4 x = *reinterpret_cast<const float4*>(Arow + cb + ch * 16 + i * 4);
-          const float4 y = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
+          const float4 x = xa[i];
+          const float4 y = yc[i];
           float4 t4 = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
                                   __uint_as_float(v[4 * i + 3]));
           if (viaQ) t4 = *reinterpret_cast<const float4*>(Qrow + cb + ch * 16 + i * 4);
@@ -592,21 +717,19 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
           const float4 v4 = uv4[tl4<32>(t, r, 64 + c)];
           const float4 g4 = *reinterpret_cast<const float4*>(gmrow + c);
           const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+          float wab4[4], wabp4[4];  // w_ab and d(w_ab)/dd for these 4 columns (packed FMAs)
+          radial_dot4(wabW, c, bek, wab4);
+          if (br == 0) radial_dot4(wabW, c, dbek, wabp4);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            float wab = 0.f;
-#pragma unroll
-            for (int k = 0; k < 9; k++) wab = fmaf(bek[k], wabW[(c + j) * 9 + k], wab);
+            const float wab = wab4[j];
             const float su = sigm_(uu[j]), oG = sigm_(vv[j]);
             const float oL = uu[j] * su;
             float g;
             if (br == 0) {
               g = gg[j] * oG * wab * (su * (1.f + uu[j] * (1.f - su)));
               // d/d w_ab -> d/d d_e through d(be)/dd (only once per column: do it in the br == 0 pass)
-              float wabp = 0.f;
-#pragma unroll
-              for (int k = 0; k < 9; k++) wabp = fmaf(dbek[k], wabW[(c + j) * 9 + k], wabp);
-              gdpart = fmaf(gg[j] * oL * oG, wabp, gdpart);
+              gdpart = fmaf(gg[j] * oL * oG, wabp4[j], gdpart);
             } else {
               g = gg[j] * oL * wab * oG * (1.f - oG);
             }
@@ -655,9 +778,13 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
       if (!viaQ) {
 #pragma unroll
         for (int i = 0; i < CPT; i++) {
-          const float* Mj = a.M + (size_t)(cb + i) * 9;
+          const float4* Mj = reinterpret_cast<const float4*>(Mrow + (cb + i) * 12);  // warp-uniform: smem broadcast
 #pragma unroll
-          for (int k = 0; k < 9; k++) gbeM[k] = fmaf(ds[i], __ldg(Mj + k), gbeM[k]);
+          for (int k4 = 0; k4 < 3; k4++) {
+            const float4 m = Mj[k4];
+            ffma2(gbeM[4 * k4], gbeM[4 * k4 + 1], ds[i], m.x, m.y);
+            ffma2(gbeM[4 * k4 + 2], gbeM[4 * k4 + 3], ds[i], m.z, m.w);
+          }
         }
       }
       if (need_gx) {
@@ -724,12 +851,14 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
 }
 
+constexpr bool kBwdPrefetchDefault = false;  // B2M_BWD_PREFETCH=1 opts in
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
   static bool attr = false;
   if (!attr) {
-    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
-    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
     attr = true;
   }
   const int64_t ntiles = (a.E + 127) / 128;
@@ -738,20 +867,30 @@ void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
     const char* v = getenv("B2M_BWD_THREADS");
     return (v && atoi(v) == 512) ? 512 : 256;  // 512 (4 threads/row, 64 regs) measured slower: LSU-bound, not warp-bound
   }();
+  static const bool pf = [] {
+    const char* v = getenv("B2M_BWD_PREFETCH");
+    return v ? atoi(v) != 0 : kBwdPrefetchDefault;
+  }();
+  AtomConvTcW wl = w;
+  wl.l2pf = l2pf_enabled();
   if (nthr == 512)
-    k_atomconv_bwd_tc<512><<<grid, 512, BwdTcSmem::bytes, st>>>(a, w);
+    k_atomconv_bwd_tc<512, false><<<grid, 512, BwdTcSmem::bytes, st>>>(a, wl);
+  else if (pf)
+    k_atomconv_bwd_tc<256, true><<<grid, 256, BwdTcSmem::bytes, st>>>(a, wl);
   else
-    k_atomconv_bwd_tc<256><<<grid, 256, BwdTcSmem::bytes, st>>>(a, w);
+    k_atomconv_bwd_tc<256, false><<<grid, 256, BwdTcSmem::bytes, st>>>(a, wl);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
 
+constexpr bool kFwdPrefetchDefault = false;  // B2M_FWD_PREFETCH=1 opts in
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
   static bool attr = false;
   if (!attr) {
-    B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
-    B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
     attr = true;
   }
   const int64_t ntiles = (a.E + 127) / 128;
@@ -760,10 +899,18 @@ void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
     const char* v = getenv("B2M_FWD_THREADS");
     return (v && atoi(v) == 512) ? 512 : 256;  // 512 (4 threads/row, 64 regs) measured slower: LSU-bound, not warp-bound
   }();
+  static const bool pf = [] {
+    const char* v = getenv("B2M_FWD_PREFETCH");
+    return v ? atoi(v) != 0 : kFwdPrefetchDefault;
+  }();
+  AtomConvTcW wl = w;
+  wl.l2pf = l2pf_enabled();
   if (nthr == 512)
-    k_atomconv_fwd_tc<512><<<grid, 512, FwdTcSmem::bytes, st>>>(a, w);
+    k_atomconv_fwd_tc<512, false><<<grid, 512, FwdTcSmem::bytes, st>>>(a, wl);
+  else if (pf)
+    k_atomconv_fwd_tc<256, true><<<grid, 256, FwdTcSmem::bytes, st>>>(a, wl);
   else
-    k_atomconv_fwd_tc<256><<<grid, 256, FwdTcSmem::bytes, st>>>(a, w);
+    k_atomconv_fwd_tc<256, false><<<grid, 256, FwdTcSmem::bytes, st>>>(a, wl);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
@@ -844,6 +991,17 @@ __global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const 
       s_a[gt] = ia;
       s_b[gt] = ib;
       s_c[gt] = ic;
+    }
+    if (w.l2pf) {
+      const int64_t tn = t + 2 * (int64_t)gridDim.x;
+      if (tn * 128 + 128 <= a.A) {
+        l2_prefetch(a.ang + tn * (128 * 64), 128 * 64 * 4, gt, 256);
+        if (gt >= 128 && gt < 140) {
+          const int which = (gt - 128) >> 2, line = (gt - 128) & 3;
+          const int* base = which == 0 ? a.a_in : which == 1 ? a.a_out : a.a_ctr;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + tn * 128 + line * 32));
+        }
+      }
     }
     gbar(g);
     const bool valid = r < nvalid;
@@ -1102,6 +1260,21 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
       s_b[gt] = ib;
       s_c[gt] = ic;
     }
+    if (w.l2pf) {
+      const int64_t tn = t + 2 * (int64_t)gridDim.x;
+      if (tn < ntiles) {
+        l2_prefetch(a.uv + tn * (128 * 128), 128 * 128 * 4, gt, 256);
+        if (HIDDEN) l2_prefetch(a.ds + tn * (128 * 128), 128 * 128 * 4, gt, 256);
+        if (tn * 128 + 128 <= a.A) {
+          l2_prefetch(a.gang + tn * (128 * 64), 128 * 64 * 4, gt, 256);
+          if (gt >= 128 && gt < 140) {
+            const int which = (gt - 128) >> 2, line = (gt - 128) & 3;
+            const int* base = which == 0 ? a.a_in : which == 1 ? a.a_out : a.a_ctr;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + tn * 128 + line * 32));
+          }
+        }
+      }
+    }
     gbar(g);
     const bool valid = r < nvalid;
     const int ib = s_b[r];
@@ -1166,9 +1339,13 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
           }
           umma_commit(&mbar[br]);
         }
+        // silu'(pre) of this branch streams in while the tensor core runs (loads issued before the wait)
+        const float4* ds4 = reinterpret_cast<const float4*>(a.ds);
+        float4 dsr[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) dsr[i] = ds4[tl4<32>(t, r, cb + i * 4)];
         mbar_wait_(&mbar[br], phase);
         tc_fence_after();
-        const float4* ds4 = reinterpret_cast<const float4*>(a.ds);
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
           uint32_t v[16];
@@ -1176,7 +1353,7 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
           tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            const float4 d4 = ds4[tl4<32>(t, r, cb + ch * 16 + i * 4)];
+            const float4 d4 = dsr[ch * 4 + i];
             gp[ch * 16 + 4 * i] = __uint_as_float(v[4 * i]) * d4.x;
             gp[ch * 16 + 4 * i + 1] = __uint_as_float(v[4 * i + 1]) * d4.y;
             gp[ch * 16 + 4 * i + 2] = __uint_as_float(v[4 * i + 2]) * d4.z;
@@ -1259,22 +1436,27 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
         gbar(g);
       }
     }
-    mbar_wait_(&mbar[3], phase);
-    tc_fence_after();
     {
+      // gang += (accumulated gpre . Wg): the read half of the read-modify-write is issued BEFORE waiting for the
+      // last GEMM (nobody else touches these 32 floats of this row during the kernel), so its latency hides behind it
+      float4* pg = reinterpret_cast<float4*>(a.gang + row * D + c0);
+      float4 o[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] = valid ? pg[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait_(&mbar[3], phase);
+      tc_fence_after();
 #pragma unroll
       for (int ch = 0; ch < 2; ch++) {
         uint32_t v[16];
         tmem_ld16(tlane + COL_G + c0 + ch * 16, v);
         tc_wait_ld();
         if (valid) {
-          float4* pg = reinterpret_cast<float4*>(a.gang + (size_t)(r0 + r) * D + c0 + ch * 16);
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            float4 o = pg[i];
-            o.x += __uint_as_float(v[4 * i]), o.y += __uint_as_float(v[4 * i + 1]);
-            o.z += __uint_as_float(v[4 * i + 2]), o.w += __uint_as_float(v[4 * i + 3]);
-            pg[i] = o;
+            float4 x = o[ch * 4 + i];
+            x.x += __uint_as_float(v[4 * i]), x.y += __uint_as_float(v[4 * i + 1]);
+            x.z += __uint_as_float(v[4 * i + 2]), x.w += __uint_as_float(v[4 * i + 3]);
+            pg[ch * 4 + i] = x;
           }
         }
       }
@@ -1298,10 +1480,12 @@ void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bo
   }
   const int64_t ntiles = (a.A + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
+  LineTcW wl = w;
+  wl.l2pf = l2pf_enabled();
   if (hidden)
-    k_line_fwd_tc<true><<<grid, 512, LineTcSmem::bytes, st>>>(a, w);
+    k_line_fwd_tc<true><<<grid, 512, LineTcSmem::bytes, st>>>(a, wl);
   else
-    k_line_fwd_tc<false><<<grid, 512, LineTcSmem::bytes, st>>>(a, w);
+    k_line_fwd_tc<false><<<grid, 512, LineTcSmem::bytes, st>>>(a, wl);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
@@ -1315,10 +1499,12 @@ void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bo
   }
   const int64_t ntiles = (a.A + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
+  LineTcW wl = w;
+  wl.l2pf = l2pf_enabled();
   if (hidden)
-    k_line_bwd_tc<true><<<grid, 512, LineTcSmem::bytes, st>>>(a, w);
+    k_line_bwd_tc<true><<<grid, 512, LineTcSmem::bytes, st>>>(a, wl);
   else
-    k_line_bwd_tc<false><<<grid, 512, LineTcSmem::bytes, st>>>(a, w);
+    k_line_bwd_tc<false><<<grid, 512, LineTcSmem::bytes, st>>>(a, wl);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
