@@ -151,10 +151,14 @@ __device__ __forceinline__ void radial_dot4(const float* WT, int col0, const flo
   }
 }
 
-static int l2pf_enabled() {  // B2M_L2_PREFETCH=0 switches the hints off (A/B measurements)
+// B2M_L2_PREFETCH: 0 = no hints, 1 (default) = atom-conv kernels only, 2 = line-graph kernels too.
+// Measured (profiles/r01c_*): in the atom-conv kernels the hints cost ~0.1 GB of extra DRAM reads per launch and buy
+// ~2 %; in the line-graph kernels (160 KB per tile, 47 MB in flight next to 1.2 GB of streamed writes) most prefetched
+// lines are evicted before use -- DRAM reads of k_line_bwd_tc<1> went from 2.06 to 3.33 GB per launch -- so they are off.
+static int l2pf_level() {
   static const int v = [] {
     const char* e = getenv("B2M_L2_PREFETCH");
-    return e ? (atoi(e) != 0 ? 1 : 0) : 1;
+    return e ? atoi(e) : 1;
   }();
   return v;
 }
@@ -521,7 +525,7 @@ struct BwdTcSmem {
   static constexpr size_t bytes = (size_t)kTotal * 4;
 };
 
-template <int NTHR, bool PF>  // PF: gathers of A[src] / C[dst] one 16-column block ahead (see the forward)
+template <int NTHR>
 __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs a, const AtomConvTcW w) {
   constexpr int NP = NTHR / 128;   // threads per row
   constexpr int CPT = 64 / NP;     // columns of each branch per thread
@@ -657,14 +661,6 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
 #pragma unroll
     for (int k = 0; k < 12; k++) gbeM[k] = 0.f;
 
-    float4 pa[4], pc[4];
-    if (PF) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        pa[i] = *reinterpret_cast<const float4*>(Arow + c0 + i * 4);
-        pc[i] = *reinterpret_cast<const float4*>(Crow + c0 + i * 4);
-      }
-    }
 #pragma unroll 1
     for (int br = 0; br < 2; br++) {
       mbar_wait_(&mbar[br], phase);
@@ -676,29 +672,12 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
         uint32_t v[16], hi[16], lo[16];
         tmem_ld16(tlane + COL_D + cb + ch * 16, v);
         tc_wait_ld();
-        float4 xa[4], yc[4];
-        if (PF) {
-#pragma unroll
-          for (int i = 0; i < 4; i++) xa[i] = pa[i], yc[i] = pc[i];
-          const int nb = ch + 1 < NCH ? cb + (ch + 1) * 16 : 64 + c0;
-          if (ch + 1 < NCH || br == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              pa[i] = *reinterpret_cast<const float4*>(Arow + nb + i * 4);
-              pc[i] = *reinterpret_cast<const float4*>(Crow + nb + i * 4);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            xa[i] = *reinterpret_cast<const float4*>(Arow + cb + ch * 16 + i * 4);
-            yc[i] = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
-          }
-        }
+        // (issuing these gathers one block ahead, as the forward does, was measured slower here: the kernel sits at
+        //  the 128-register limit and the prefetched rows spill)
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          const float4 x = xa[i];
-          const float4 y = yc[i];
+          const float4 x = *reinterpret_cast<const float4*>(Arow + cb + ch * 16 + i * 4);
+          const float4 y = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
           float4 t4 = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
                                   __uint_as_float(v[4 * i + 3]));
           if (viaQ) t4 = *reinterpret_cast<const float4*>(Qrow + cb + ch * 16 + i * 4);
@@ -851,14 +830,12 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
 }
 
-constexpr bool kBwdPrefetchDefault = false;  // B2M_BWD_PREFETCH=1 opts in
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
   static bool attr = false;
   if (!attr) {
-    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
-    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
-    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
+    B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
     attr = true;
   }
   const int64_t ntiles = (a.E + 127) / 128;
@@ -867,23 +844,17 @@ void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
     const char* v = getenv("B2M_BWD_THREADS");
     return (v && atoi(v) == 512) ? 512 : 256;  // 512 (4 threads/row, 64 regs) measured slower: LSU-bound, not warp-bound
   }();
-  static const bool pf = [] {
-    const char* v = getenv("B2M_BWD_PREFETCH");
-    return v ? atoi(v) != 0 : kBwdPrefetchDefault;
-  }();
   AtomConvTcW wl = w;
-  wl.l2pf = l2pf_enabled();
+  wl.l2pf = l2pf_level() >= 1;
   if (nthr == 512)
-    k_atomconv_bwd_tc<512, false><<<grid, 512, BwdTcSmem::bytes, st>>>(a, wl);
-  else if (pf)
-    k_atomconv_bwd_tc<256, true><<<grid, 256, BwdTcSmem::bytes, st>>>(a, wl);
+    k_atomconv_bwd_tc<512><<<grid, 512, BwdTcSmem::bytes, st>>>(a, wl);
   else
-    k_atomconv_bwd_tc<256, false><<<grid, 256, BwdTcSmem::bytes, st>>>(a, wl);
+    k_atomconv_bwd_tc<256><<<grid, 256, BwdTcSmem::bytes, st>>>(a, wl);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
 
-constexpr bool kFwdPrefetchDefault = false;  // B2M_FWD_PREFETCH=1 opts in
+constexpr bool kFwdPrefetchDefault = true;  // measured: 1.087 vs 1.122 ms per launch; B2M_FWD_PREFETCH=0 switches it off
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
   static bool attr = false;
@@ -904,7 +875,7 @@ void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
     return v ? atoi(v) != 0 : kFwdPrefetchDefault;
   }();
   AtomConvTcW wl = w;
-  wl.l2pf = l2pf_enabled();
+  wl.l2pf = l2pf_level() >= 1;
   if (nthr == 512)
     k_atomconv_fwd_tc<512, false><<<grid, 512, FwdTcSmem::bytes, st>>>(a, wl);
   else if (pf)
@@ -1481,7 +1452,7 @@ void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bo
   const int64_t ntiles = (a.A + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
   LineTcW wl = w;
-  wl.l2pf = l2pf_enabled();
+  wl.l2pf = l2pf_level() >= 2;
   if (hidden)
     k_line_fwd_tc<true><<<grid, 512, LineTcSmem::bytes, st>>>(a, wl);
   else
@@ -1500,7 +1471,7 @@ void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bo
   const int64_t ntiles = (a.A + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
   LineTcW wl = w;
-  wl.l2pf = l2pf_enabled();
+  wl.l2pf = l2pf_level() >= 2;
   if (hidden)
     k_line_bwd_tc<true><<<grid, 512, LineTcSmem::bytes, st>>>(a, wl);
   else
