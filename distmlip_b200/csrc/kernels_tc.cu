@@ -1626,6 +1626,162 @@ __global__ void __launch_bounds__(256, 2)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
 }
 
+// Software-pipelined variant (opt-in, B2M_GEMM_PIPE=1; written after the round's GPU budget was spent, so it is NOT the
+// default until it has passed the GPU suite): the A chunk of the NEXT (tile, K-half) is loaded into registers while the
+// current one is converted, multiplied and written back, and the accumulate / residual rows of an output slab are
+// requested before the TMEM read-back, so that no global load is waited for right after it is issued.
+template <int K, int N>
+__global__ void __launch_bounds__(256, 2)
+    k_gemm_tc_pipe(const float* __restrict__ A, int lda, const float* __restrict__ Bcan, float* __restrict__ C, int ldc,
+                   int M, const float* __restrict__ bias, const float* __restrict__ R, int ldr, int accum) {
+  constexpr uint32_t COL_D = 128;
+  constexpr uint32_t LBO = (N / 8) * 128;
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+  constexpr int PITCH = 68;
+  constexpr int KH = K / 64;
+  extern __shared__ __align__(1024) float smem[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + 4);
+  float* Bs = smem + 64;
+  float* stg = Bs + 2 * N * K;  // [128][68]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int r = q * 32 + lane;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init_(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int ntiles = (M + 127) / 128;
+  // my cooperative-copy coordinates: 8 float4 per thread, rows rr0 + 16*i, 16-byte column c4
+  const int rr0 = tid >> 4, c4 = tid & 15;
+  float4 pre[8];
+  auto load_chunk = [&](int t, int kh) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int row = t * 128 + rr0 + 16 * i;
+      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < M) pre[i] = *reinterpret_cast<const float4*>(A + (size_t)row * lda + kh * 64 + c4 * 4);
+    }
+  };
+  if ((int)blockIdx.x < ntiles) load_chunk(blockIdx.x, 0);  // in flight while the weights are staged
+  for (int i = tid; i < 2 * N * K / 4; i += 256) reinterpret_cast<float4*>(Bs)[i] = reinterpret_cast<const float4*>(Bcan)[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tptr;
+  const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+  const uint32_t b_addr = s_u32(Bs);
+  uint32_t phase = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int row0 = t * 128;
+#pragma unroll 1
+    for (int kh = 0; kh < KH; kh++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) *reinterpret_cast<float4*>(stg + (rr0 + 16 * i) * PITCH + c4 * 4) = pre[i];
+      // next chunk: the other K half of this tile, or the first half of my next tile
+      if (kh + 1 < KH)
+        load_chunk(t, kh + 1);
+      else if (t + (int)gridDim.x < ntiles)
+        load_chunk(t + gridDim.x, 0);
+      __syncthreads();
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float4 x = *reinterpret_cast<const float4*>(stg + r * PITCH + half * 32 + ch * 16 + i * 4);
+          const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t h = tf32_hi_bits(xv[j]);
+            hi[4 * i + j] = h;
+            lo[4 * i + j] = __float_as_uint(xv[j] - __uint_as_float(h));
+          }
+        }
+        tmem_st16(tlane + half * 32 + ch * 16, hi);
+        tmem_st16(tlane + 64 + half * 32 + ch * 16, lo);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        uint32_t acc = kh == 0 ? 0u : 1u;
+#pragma unroll
+        for (int term = 0; term < 3; term++) {
+          const uint32_t acol = term == 1 ? 64u : 0u;
+          const uint32_t bsel = b_addr + (term == 2 ? (uint32_t)(N * K) * 4u : 0u) + (uint32_t)kh * 16u * LBO;
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) {
+            umma_ts(tbase + COL_D, tbase + acol + ks * 8, umma_desc(bsel + ks * 2 * LBO, LBO, 128u), IDESC, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(mbar);
+      }
+      mbar_wait_(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int nh = 0; nh < N / 64; nh++) {
+      // rows this slab adds to the product (residual R, or C itself when accumulating): requested before the read-back
+      const float* addsrc = R ? R : (accum ? C : nullptr);
+      const int addld = R ? ldr : ldc;
+      float4 add[8];
+      if (addsrc) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int row = row0 + rr0 + 16 * i;
+          add[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < M) add[i] = *reinterpret_cast<const float4*>(addsrc + (size_t)row * addld + nh * 64 + c4 * 4);
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t v[16];
+        tmem_ld16(tlane + COL_D + nh * 64 + half * 32 + ch * 16, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          *reinterpret_cast<float4*>(stg + r * PITCH + half * 32 + ch * 16 + i * 4) =
+              make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                          __uint_as_float(v[4 * i + 3]));
+      }
+      tc_fence_before();
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int rr = rr0 + 16 * i;
+        const int row = row0 + rr, col = nh * 64 + c4 * 4;
+        if (row < M) {
+          float4 o = *reinterpret_cast<const float4*>(stg + rr * PITCH + c4 * 4);
+          if (bias) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + col);
+            o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+          }
+          if (addsrc) o.x += add[i].x, o.y += add[i].y, o.z += add[i].z, o.w += add[i].w;
+          float4* cp = reinterpret_cast<float4*>(C + (size_t)row * ldc + col);
+          if (R && accum) {  // both at once (not used by the engine): the accumulate read stays in place
+            const float4 c = *cp;
+            o.x += c.x, o.y += c.y, o.z += c.z, o.w += c.w;
+          }
+          *cp = o;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
+}
+
 template <int K, int N>
 static void launch_gemm_tc_t(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M,
                              const float* bias, const float* R, int ldr, bool accum, int num_sms) {
@@ -1635,9 +1791,21 @@ static void launch_gemm_tc_t(cudaStream_t st, const float* A, int lda, const flo
     B2M_CK(cudaFuncSetAttribute(k_gemm_tc<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     attr = true;
   }
+  static const bool pipe = [] {
+    const char* v = getenv("B2M_GEMM_PIPE");
+    return v && atoi(v) != 0;
+  }();
+  static bool attr_pipe = false;
+  if (pipe && !attr_pipe) {
+    B2M_CK(cudaFuncSetAttribute(k_gemm_tc_pipe<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    attr_pipe = true;
+  }
   const int ntiles = (M + 127) / 128;
   const int grid = std::min(ntiles, 2 * num_sms);
-  k_gemm_tc<K, N><<<grid, 256, bytes, st>>>(A, lda, Bcan, C, ldc, M, bias, R, ldr, accum ? 1 : 0);
+  if (pipe)
+    k_gemm_tc_pipe<K, N><<<grid, 256, bytes, st>>>(A, lda, Bcan, C, ldc, M, bias, R, ldr, accum ? 1 : 0);
+  else
+    k_gemm_tc<K, N><<<grid, 256, bytes, st>>>(A, lda, Bcan, C, ldc, M, bias, R, ldr, accum ? 1 : 0);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
