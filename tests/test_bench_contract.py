@@ -57,7 +57,7 @@ def test_clock_sampler_windows(tmp_path, monkeypatch):
     s.start()
     assert s.rows, "start() must wait for the first row (NVML start-up stays outside the timed region)"
     t0 = time.perf_counter()
-    time.sleep(0.3)
+    time.sleep(1.0)  # ~20 rows at the 50 ms cadence; generous so that a loaded CI host still sees >= 2
     t1 = time.perf_counter()
     c = s.stop([("timed", t0, t1), ("e2e", t1, t1 + 1)])
     assert c["window"] == "timed" and c["samples"] >= 2
@@ -67,7 +67,7 @@ def test_clock_sampler_windows(tmp_path, monkeypatch):
     s.start()
     t0 = time.perf_counter()
     t2 = time.perf_counter()
-    time.sleep(0.3)
+    time.sleep(1.0)
     t3 = time.perf_counter()
     c = s.stop([("timed", t0, t0), ("e2e", t2, t3)])
     assert c["window"] == "timed+e2e" and c["samples"] >= 2
