@@ -63,6 +63,23 @@ def test_energy_forces_stress_match_oracle(eng, model, n):
     check_vs_oracle(eng, model, si_diamond(n))
 
 
+def test_many_tiles_per_cta_match_oracle(eng, model):
+    """8 000 atoms = 1 750 edge tiles and 750 angle tiles: every persistent CTA (grid = 2 x 148) runs 5-6 tiles, so the
+    mbarrier phase flips, the TMEM reuse across tiles and the destination runs that straddle tile boundaries are checked
+    against the oracle directly (not only through self-consistency properties)."""
+    atoms = si_diamond(10, seed=31)
+    check_vs_oracle(eng, model, atoms)
+    c = eng.counts()
+    assert c["n_edges"] // 128 > 5 * 2 * 148 and c["n_angles"] // 128 > 2 * 148
+
+
+def test_rough_cell_8000_matches_oracle(eng, model):
+    """degree-imbalanced structure (random sequential addition): 0-12 bonds and 10-40 edges per atom, so
+    destination runs of every length occur inside and across tiles; > 5 tiles per CTA."""
+    atoms = rough_cell(8000, seed=11)
+    check_vs_oracle(eng, model, atoms)
+
+
 def test_stage_taps_match_manual_mirror(eng, model):
     atoms = si_diamond(3)
     og = oracle_graph(atoms)
