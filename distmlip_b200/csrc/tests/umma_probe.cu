@@ -1,7 +1,10 @@
 // umma_probe.cu -- standalone probe of the tcgen05 TF32 path used by the fused kernels:
 //   D[128x64] (TMEM, fp32) = A[128x64] * B[64x64]^T   with B = W[n][k] (K-major, no swizzle) in smem and
 //   A either in smem (SS) or in TMEM written with tcgen05.st (TS).  Also the 3xTF32 split variant.
-// usage: umma_probe <mode: 0=SS 1=TS> <swap lbo/sbo: 0|1> <split: 0|1>
+// usage: umma_probe <mode: 0=SS 1=TS> <swap lbo/sbo: 0|1> <split: 0|1> [bmajor lbo_b sbo_b kstep_b]
+//   bmajor=1: the SAME smem image of W (canonical K-major [n][k]) is read as an MN-major B operand, i.e. the product
+//   D = A * W (W^T as the B operand without a second, transposed copy of the weights); lbo_b / sbo_b / kstep_b are the
+//   descriptor byte offsets to try (expected: 128, 1024, 128).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -33,7 +36,8 @@ __device__ __forceinline__ float tf32_hi(float x) {
 
 __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const float* __restrict__ Afmt,
                                              const float* __restrict__ Bfmt, float* __restrict__ D, uint32_t lbo_b,
-                                             uint32_t sbo_b, uint32_t lbo_a, uint32_t sbo_a, int use_ts, int split) {
+                                             uint32_t sbo_b, uint32_t lbo_a, uint32_t sbo_a, int use_ts, int split, int bmajor,
+                                             uint32_t kstep_b) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* Bs = reinterpret_cast<float*>(smem);              // 2 x 16 KB (hi, lo)
   float* As = reinterpret_cast<float*>(smem + 32768);      // 2 x 32 KB (hi, lo)   (SS mode)
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const 
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // instruction descriptor: c=F32 (1<<4), a=TF32 (2<<7), b=TF32 (2<<10), K-major both, N=64 (8<<17), M=128 (8<<24)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (8u << 17) | (8u << 24) | (bmajor ? (1u << 16) : 0u);
     const uint32_t bs_hi = smem_u32(Bs), bs_lo = smem_u32(Bs + 4096);
     const uint32_t as_hi = smem_u32(As), as_lo = smem_u32(As + 8192);
     int first = 1;
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ A, const 
       const uint32_t acol = term == 1 ? col_alo : col_ahi;
       const uint32_t asel = term == 1 ? as_lo : as_hi;
       for (int ks = 0; ks < 8; ks++) {
-        const uint64_t bdesc = make_desc(bsel + ks * 2 * lbo_b, lbo_b, sbo_b);
+        const uint64_t bdesc = make_desc(bsel + ks * kstep_b, lbo_b, sbo_b);
         const uint32_t acc = first ? 0u : 1u;
         first = 0;
         if (use_ts) {
@@ -161,6 +165,7 @@ int main(int argc, char** argv) {
   const int use_ts = argc > 1 ? atoi(argv[1]) : 1;
   const int swap = argc > 2 ? atoi(argv[2]) : 0;
   const int split = argc > 3 ? atoi(argv[3]) : 0;
+  const int bmajor = argc > 4 ? atoi(argv[4]) : 0;
   std::vector<float> A(128 * 64), W(64 * 64), Dref(128 * 64), D(128 * 64);
   srand(1);
   for (auto& x : A) x = (rand() / (float)RAND_MAX - 0.5f) * 2.f;
@@ -168,7 +173,7 @@ int main(int argc, char** argv) {
   for (int m = 0; m < 128; m++)
     for (int n = 0; n < 64; n++) {
       double s = 0;
-      for (int k = 0; k < 64; k++) s += (double)A[m * 64 + k] * (double)W[n * 64 + k];
+      for (int k = 0; k < 64; k++) s += (double)A[m * 64 + k] * (double)(bmajor ? W[k * 64 + n] : W[n * 64 + k]);
       Dref[m * 64 + n] = (float)s;
     }
   // canonical K-major no-swizzle: element (r, k) at ((k/4) * (R/8) + r/8) * 32 floats + (r%8)*4 + k%4
@@ -210,9 +215,11 @@ int main(int argc, char** argv) {
     lbo_a = sbo_a;
     sbo_a = t;
   }
+  uint32_t kstep_b = 2 * lbo_b;
+  if (argc > 7) lbo_b = atoi(argv[5]), sbo_b = atoi(argv[6]), kstep_b = atoi(argv[7]);
   const size_t smem = 32768 + 65536 + 64;
   CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  probe<<<1, 128, smem>>>(dA, dAf, dBf, dD, lbo_b, sbo_b, lbo_a, sbo_a, use_ts, split);
+  probe<<<1, 128, smem>>>(dA, dAf, dBf, dD, lbo_b, sbo_b, lbo_a, sbo_a, use_ts, split, bmajor, kstep_b);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
@@ -221,6 +228,7 @@ int main(int argc, char** argv) {
     maxerr = fmax(maxerr, fabs((double)D[i] - (double)Dref[i]));
     maxref = fmax(maxref, fabs((double)Dref[i]));
   }
+  printf("bmajor=%d lbo_b=%u sbo_b=%u kstep_b=%u ", bmajor, lbo_b, sbo_b, kstep_b);
   printf("mode=%s swap=%d split=%d  max|err|=%.3e  max|ref|=%.3e  D[0]=%f ref=%f  D[last]=%f ref=%f\n",
          use_ts ? "TS" : "SS", swap, split, maxerr, maxref, D[0], Dref[0], D.back(), Dref.back());
   return 0;

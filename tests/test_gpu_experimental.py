@@ -17,7 +17,7 @@ pytestmark = [pytest.mark.gpu,
 
 SWITCHES = [
     {"B2M_ATOMCONV_V2": "1"},
-    {"B2M_GEMM_PIPE": "1"},
+    {"B2M_GEMM_PIPE": "0"},
     {"B2M_L2_PREFETCH": "2"},
     {"B2M_L2_PREFETCH": "0"},
     {"B2M_FWD_PREFETCH": "0"},
