@@ -129,6 +129,10 @@ class Engine:
                                                a.ndim))
 
     def set_element_refs(self, offsets):
+        """per-element energy offsets (double); None clears offsets set by an earlier Potential_Dist"""
+        if offsets is None:
+            self._ck(self.lib.b2m_set_element_refs(self.h, None, 0))
+            return
         a = np.ascontiguousarray(offsets, dtype=np.float64)
         self._ck(self.lib.b2m_set_element_refs(self.h, a.ctypes.data_as(C.POINTER(C.c_double)), len(a)))
 

@@ -58,6 +58,19 @@ struct DBuf {
   void zero(size_t n, cudaStream_t s) { B2M_CK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: guards are per device so that a
+// second engine on another GPU of the same process sets them again.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 extern long long g_launch_count;  // kernels launched by this library (bench.py gpu_launches)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

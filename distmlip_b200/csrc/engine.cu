@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -85,14 +86,17 @@ struct b2m_engine {
   // weights
   std::map<std::string, std::vector<float>> host_w;
   std::map<std::string, std::vector<int64_t>> host_shape;
+  std::set<std::string> consumed;  // state_dict keys finalize_weights actually used
   std::vector<double> elem_refs;
+  DBuf<double> erefbuf;
   bool finalized = false;
   DBuf<float> wbuf;
   std::vector<AtomLayerW> aw;
   std::vector<BondLayerW> bw;
   float *d_emb = nullptr, *d_Wbe = nullptr, *d_Wae = nullptr, *d_Wabw = nullptr, *d_W3bw = nullptr, *d_fa = nullptr;
   float *d_F0k = nullptr, *d_c0 = nullptr, *d_F0raw = nullptr, *d_F1k = nullptr, *d_c1 = nullptr, *d_F1raw = nullptr,
-        *d_F2 = nullptr, *d_Ws = nullptr, *d_eref = nullptr;
+        *d_F2 = nullptr, *d_Ws = nullptr;
+  const double* d_eref = nullptr;  // per-element energy offsets, double like the energy accumulator
   float c2 = 0.f, bs = 0.f;
   RadialParams rp2, rp3;
   // comm
@@ -122,6 +126,7 @@ struct b2m_engine {
   std::map<const float*, const float*> canon_of;  // FFMA-layout GEMM operand -> canonical tcgen05 copy
   int num_sms = 148;
   bool use_tc = true;  // tcgen05 kernels; B2M_LEGACY_FFMA=1 selects the FP32-FFMA tile kernels (A/B checks)
+  int ac_gen = 1;      // atom-conv kernel generation on the tcgen05 path (B2M_ATOMCONV=1|3)
 };
 
 namespace b2m {
@@ -129,6 +134,7 @@ namespace b2m {
 static const std::vector<float>& W(b2m_engine* e, const std::string& k, std::vector<int64_t> shape) {
   auto it = e->host_w.find(k);
   B2M_REQUIRE(it != e->host_w.end(), B2M_ERR_INVALID, "missing weight: " + k);
+  e->consumed.insert(k);
   const auto& sh = e->host_shape[k];
   size_t n = 1;
   for (auto s : shape) n *= (size_t)s;
@@ -211,6 +217,7 @@ static void finalize_weights(b2m_engine* e) {
     B2M_REQUIRE(!bad, B2M_ERR_INVALID,
                 "unsupported CHGNet option (bond_update_hidden_dims / layer_bond_weights / state / norm): " + k);
   }
+  e->consumed.clear();
   Packer P;
   std::map<std::string, size_t> off;
   std::vector<std::string> gemm_names;
@@ -364,9 +371,18 @@ static void finalize_weights(b2m_engine* e) {
   e->c2 = W(e, "final_layer.layers.2.bias", {1})[0];
   put("Ws", W(e, "sitewise_readout.weight", {1, D}));
   e->bs = W(e, "sitewise_readout.bias", {1})[0];
+  // every tensor of the state_dict must have been used: an extra bias / normalisation / per-layer weight function of
+  // a non-default CHGNet configuration would otherwise be dropped silently and give wrong energies.
+  // bond_bond_weights is part of the default model but feeds only the (absent) bond update of the atom graph.
+  for (auto& kv : e->host_w) {
+    if (e->consumed.count(kv.first) || kv.first == "bond_bond_weights.weight") continue;
+    throw Error(B2M_ERR_INVALID, "state_dict tensor '" + kv.first +
+                                     "' is not used by this engine (unsupported CHGNet configuration; refusing to ignore it)");
+  }
   if (!e->elem_refs.empty()) {
-    std::vector<float> r(e->elem_refs.begin(), e->elem_refs.end());
-    put("eref", r);
+    e->erefbuf.ensure(e->elem_refs.size());
+    B2M_CK(cudaMemcpyAsync(e->erefbuf.p, e->elem_refs.data(), e->elem_refs.size() * sizeof(double), cudaMemcpyHostToDevice,
+                           e->st));
   }
   e->wbuf.ensure(P.host.size() + 64);
   B2M_CK(cudaMemcpyAsync(e->wbuf.p, P.host.data(), P.host.size() * sizeof(float), cudaMemcpyHostToDevice, e->st));
@@ -383,7 +399,7 @@ static void finalize_weights(b2m_engine* e) {
   e->d_F0k = dp("F0k"), e->d_F0raw = dp("F0raw"), e->d_c0 = dp("c0");
   e->d_F1k = dp("F1k"), e->d_F1raw = dp("F1raw"), e->d_c1 = dp("c1");
   e->d_F2 = dp("F2"), e->d_Ws = dp("Ws");
-  e->d_eref = e->elem_refs.empty() ? nullptr : dp("eref");
+  e->d_eref = e->elem_refs.empty() ? nullptr : e->erefbuf.p;
   e->aw.resize(nb);
   for (int l = 0; l < nb; l++) {
     const std::string q = "a" + std::to_string(l) + ".";
@@ -562,7 +578,10 @@ static void atom_layer_fwd(b2m_engine* e, int l) {
   if (e->use_tc) {
     AtomConvTcW tw{w.W2can, w.Mcan, w.W2Tcan};
     a.uv_save = e->want_grads ? e->uv[l].p : nullptr;
-    launch_atomconv_fwd_tc(e->st, a, tw, e->num_sms);
+    if (e->ac_gen >= 3)
+      launch_atomconv_fwd_v3(e->st, a, tw, e->num_sms);
+    else
+      launch_atomconv_fwd_tc(e->st, a, tw, e->num_sms);
   } else {
     launch_atomconv_fwd(e->st, a);
   }
@@ -851,6 +870,8 @@ int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_han
     {
       const char* leg = getenv("B2M_LEGACY_FFMA");
       e->use_tc = !(leg && leg[0] == '1');
+      const char* gen = getenv("B2M_ATOMCONV");
+      e->ac_gen = gen ? atoi(gen) : 1;
     }
     B2M_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     for (auto& ev : e->ev) B2M_CK(cudaEventCreate(&ev));
@@ -893,8 +914,13 @@ int b2m_load_weights(b2m_handle h, const char* name, const float* host_ptr, cons
 
 int b2m_set_element_refs(b2m_handle h, const double* offsets, int n) {
   API_BEGIN
-  B2M_REQUIRE(offsets && n == h->desc.n_elem, B2M_ERR_INVALID, "element_refs length must equal n_elem");
-  h->elem_refs.assign(offsets, offsets + n);
+  if (offsets == nullptr || n == 0) {  // clear: a later Potential without element_refs must not inherit the old offsets
+    h->elem_refs.clear();
+    h->d_eref = nullptr;
+  } else {
+    B2M_REQUIRE(n == h->desc.n_elem, B2M_ERR_INVALID, "element_refs length must equal n_elem");
+    h->elem_refs.assign(offsets, offsets + n);
+  }
   h->finalized = false;
   API_END
 }

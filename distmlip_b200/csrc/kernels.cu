@@ -488,10 +488,9 @@ __global__ void __launch_bounds__(NT, 2) k_atomconv_fwd(const AtomConvArgs a) {
 
 void launch_atomconv_fwd(cudaStream_t st, const AtomConvArgs& a) {
   if (a.E <= 0) return;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtomSmemFwd::bytes));
-    attr = true;
   }
   k_atomconv_fwd<<<cdiv(a.E, TM), NT, AtomSmemFwd::bytes, st>>>(a);
   B2M_CK(cudaGetLastError());
@@ -708,10 +707,9 @@ __global__ void __launch_bounds__(NT, 1) k_atomconv_bwd(const AtomConvArgs a) {
 
 void launch_atomconv_bwd(cudaStream_t st, const AtomConvArgs& a) {
   if (a.E <= 0) return;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtomSmemBwd::bytes));
-    attr = true;
   }
   k_atomconv_bwd<<<cdiv(a.E, TM), NT, AtomSmemBwd::bytes, st>>>(a);
   B2M_CK(cudaGetLastError());
@@ -1014,11 +1012,10 @@ __global__ void __launch_bounds__(NT, 1) k_line_bwd(const LineArgs a) {
 
 void launch_line_fwd(cudaStream_t st, const LineArgs& a, bool hidden) {
   if (a.A <= 0) return;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     B2M_CK(cudaFuncSetAttribute(k_line_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineSmem::fwd_bytes));
     B2M_CK(cudaFuncSetAttribute(k_line_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineSmem::fwd_bytes));
-    attr = true;
   }
   if (hidden)
     k_line_fwd<true><<<cdiv(a.A, TM), NT, LineSmem::fwd_bytes, st>>>(a);
@@ -1029,11 +1026,10 @@ void launch_line_fwd(cudaStream_t st, const LineArgs& a, bool hidden) {
 }
 void launch_line_bwd(cudaStream_t st, const LineArgs& a, bool hidden) {
   if (a.A <= 0) return;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     B2M_CK(cudaFuncSetAttribute(k_line_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineSmem::bwd_bytes));
     B2M_CK(cudaFuncSetAttribute(k_line_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineSmem::bwd_bytes));
-    attr = true;
   }
   if (hidden)
     k_line_bwd<true><<<cdiv(a.A, TM), NT, LineSmem::bwd_bytes, st>>>(a);
@@ -1192,7 +1188,7 @@ void launch_angle_init_bwd(cudaStream_t st, int64_t na, const int* a_in, const i
 // ============================================================================================
 __global__ void __launch_bounds__(256) k_rowdot(int n, const float* __restrict__ X, const float* __restrict__ w,
                                                 float bias, float* __restrict__ out, double* __restrict__ sum,
-                                                const int* __restrict__ type, const float* __restrict__ elem_ref,
+                                                const int* __restrict__ type, const double* __restrict__ elem_ref,
                                                 float scale) {
   // one warp per row
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1209,7 +1205,7 @@ __global__ void __launch_bounds__(256) k_rowdot(int n, const float* __restrict__
     v += bias;
     if (out) out[warp] = v;
     contrib = (double)scale * (double)v;
-    if (elem_ref) contrib += (double)elem_ref[type[warp]];
+    if (elem_ref) contrib += elem_ref[type[warp]];
   }
   if (sum) {
     if (lane == 0) part[threadIdx.x >> 5] = contrib;
@@ -1222,7 +1218,7 @@ __global__ void __launch_bounds__(256) k_rowdot(int n, const float* __restrict__
   }
 }
 void launch_rowdot(cudaStream_t st, int n, const float* X, const float* w, float bias, float* out, double* sum,
-                   const int* type, const float* elem_ref, float scale) {
+                   const int* type, const double* elem_ref, float scale) {
   if (n <= 0) return;
   k_rowdot<<<cdiv((int64_t)n * 32, 256), 256, 0, st>>>(n, X, w, bias, out, sum, type, elem_ref, scale);
   B2M_CK(cudaGetLastError());

@@ -120,7 +120,7 @@ void launch_angle_init_bwd(cudaStream_t st, int64_t na, const int* a_in, const i
 // -------- readout --------
 // e_atom = y2 @ F2 + c2 (+elem ref); energy (double) += sum; site = x @ Ws + bs
 void launch_rowdot(cudaStream_t st, int n, const float* X, const float* w, float bias, float* out, double* sum,
-                   const int* type, const float* elem_ref, float scale);
+                   const int* type, const double* elem_ref, float scale);
 // g[r][c] = scale * w[c] * dsilu(pre[r][c])
 void launch_readout_seed(cudaStream_t st, int n, const float* pre, const float* w, float scale, float* g);
 
@@ -152,6 +152,8 @@ struct AtomConvTcW {
 };
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
+// third generation (kernels_ac3.cu): cp.async-staged gathers one tile ahead, no saved pre-activations unless uv_save
+void launch_atomconv_fwd_v3(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
 // C[M,N] = (R | accum C | 0) + A[M,K] @ B + bias, B given as canonical hi/lo planes of its [N][K] view.
 // (K,N) in {(64,128), (64,64), (128,64)}.
 void launch_gemm_tc(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M, int N,

@@ -1301,11 +1301,10 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_bwd_v2(const AtomConvArgs a
 
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
-    attr = true;
   }
   const int64_t ntiles = (a.E + 127) / 128;
   const int grid = (int)std::min<int64_t>(ntiles, 2 * (int64_t)num_sms);
@@ -1318,10 +1317,9 @@ void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
     return v && atoi(v) != 0;
   }();
   if (v2) {
-    static bool attr2 = false;
-    if (!attr2) {
+    static PerDeviceOnce attr2;
+    if (attr2.first()) {
       B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdV2Smem::bytes));
-      attr2 = true;
     }
     const int grid2 = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
     k_atomconv_bwd_v2<<<grid2, 512, BwdV2Smem::bytes, st>>>(a, w);
@@ -1342,12 +1340,11 @@ void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
 constexpr bool kFwdPrefetchDefault = true;  // measured: 1.087 vs 1.122 ms per launch; B2M_FWD_PREFETCH=0 switches it off
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
-    attr = true;
   }
   const int64_t ntiles = (a.E + 127) / 128;
   const int grid = (int)std::min<int64_t>(ntiles, 2 * (int64_t)num_sms);
@@ -1364,10 +1361,9 @@ void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
     return v && atoi(v) != 0;
   }();
   if (v2) {
-    static bool attr2 = false;
-    if (!attr2) {
+    static PerDeviceOnce attr2;
+    if (attr2.first()) {
       B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdV2Smem::bytes));
-      attr2 = true;
     }
     const int grid2 = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
     k_atomconv_fwd_v2<<<grid2, 512, FwdV2Smem::bytes, st>>>(a, w);
@@ -1943,11 +1939,10 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
 
 void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms) {
   if (a.A <= 0) return;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     B2M_CK(cudaFuncSetAttribute(k_line_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_line_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
-    attr = true;
   }
   const int64_t ntiles = (a.A + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
@@ -1962,11 +1957,10 @@ void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bo
 }
 void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms) {
   if (a.A <= 0) return;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     B2M_CK(cudaFuncSetAttribute(k_line_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_line_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
-    attr = true;
   }
   const int64_t ntiles = (a.A + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
@@ -2286,19 +2280,17 @@ template <int K, int N>
 static void launch_gemm_tc_t(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M,
                              const float* bias, const float* R, int ldr, bool accum, int num_sms) {
   constexpr size_t bytes = (size_t)(64 + 2 * N * K + 128 * 68) * 4;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     B2M_CK(cudaFuncSetAttribute(k_gemm_tc<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    attr = true;
   }
   static const bool pipe = [] {
     const char* v = getenv("B2M_GEMM_PIPE");
     return v ? atoi(v) != 0 : true;
   }();
-  static bool attr_pipe = false;
-  if (pipe && !attr_pipe) {
+  static PerDeviceOnce attr_pipe;
+  if (pipe && attr_pipe.first()) {
     B2M_CK(cudaFuncSetAttribute(k_gemm_tc_pipe<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    attr_pipe = true;
   }
   const int ntiles = (M + 127) / 128;
   const int grid = std::min(ntiles, 2 * num_sms);

@@ -89,6 +89,13 @@ class CHGNet_Dist:
             raise NotImplementedError("State features not implemented for distributed computation.")
         if self._attr("readout_field", "atom_feat") not in ("atom_feat", "node_feat"):
             raise NotImplementedError("only atom_feat readout is supported (chgnet.py:442-449)")
+        # the kernels hard-code SiLU hidden activations with a sigmoid gate and a sum readout (chgnet.py:436-438 honours
+        # self.readout_operation; matgl's default activation_type is "swish")
+        act = self._attr("activation_type", "swish")
+        if isinstance(act, str) and act.lower() not in ("swish", "silu"):
+            raise NotImplementedError(f"activation_type={act!r}: the engine implements swish/SiLU only")
+        if str(self._attr("readout_operation", "sum")).lower() != "sum":
+            raise NotImplementedError("readout_operation must be 'sum' (the engine sums atomic energies)")
         eng = _lib.Engine(
             n_elem=int(sd["atom_embedding.weight"].shape[0]), dim=dim, max_n=max_n, max_f=max_f,
             n_blocks=int(self._attr("n_blocks")), cutoff=float(self._attr("cutoff")),
@@ -135,8 +142,7 @@ class CHGNet_Dist:
         if self._engine_finalized and key == self._final_key:
             return
         eng.set_scaling(key[0], key[1])
-        if element_refs is not None:
-            eng.set_element_refs(np.ravel(element_refs))
+        eng.set_element_refs(None if element_refs is None else np.ravel(element_refs))
         eng.finalize()
         self._engine_finalized, self._final_key = True, key
 

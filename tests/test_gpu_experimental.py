@@ -16,6 +16,7 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("B2M_TEST_EXPERIMENTAL") != "1", reason="opt-in: B2M_TEST_EXPERIMENTAL=1")]
 
 SWITCHES = [
+    {"B2M_ATOMCONV": "3"},
     {"B2M_ATOMCONV_V2": "1"},
     {"B2M_GEMM_PIPE": "0"},
     {"B2M_L2_PREFETCH": "2"},
