@@ -368,7 +368,7 @@ def run_ours(args):
             "parity": parity,
             "e2e": {"value": e2e_val, "unit": "atoms/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": natoms * (24 + 4) + 72 + 12, "d2h_bytes_per_step": natoms * 12 + 8 + 36 + natoms * 4},
-            "roofline": {"bound": "hbm", "kernel": "k_atomconv_fwd_tc (edge gather, tcgen05)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "k_atomconv_fwd_v3 (edge gather: cp.async-staged A[src] rows, tcgen05 3xTF32)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "bytes_per_launch": alg_bytes, "bytes_convention": "SURVEY 8(d): 314 B/edge",
                          "kernel_ms": g_ms, "achieved_own_layout": own_bytes / (g_ms * 1e-3) / 1e9,

@@ -126,7 +126,8 @@ struct b2m_engine {
   std::map<const float*, const float*> canon_of;  // FFMA-layout GEMM operand -> canonical tcgen05 copy
   int num_sms = 148;
   bool use_tc = true;  // tcgen05 kernels; B2M_LEGACY_FFMA=1 selects the FP32-FFMA tile kernels (A/B checks)
-  int ac_gen = 1;      // atom-conv kernel generation on the tcgen05 path (B2M_ATOMCONV=1|3)
+  int ac_gen = 3;      // atom-conv kernel generation on the tcgen05 path: 3 (default, kernels_ac3.cu), 1 = first generation,
+                       // 4 = third-generation forward with the first-generation backward (B2M_ATOMCONV, A/B checks)
 };
 
 namespace b2m {
@@ -607,7 +608,10 @@ static void atom_layer_bwd(b2m_engine* e, int l) {
   if (e->use_tc) {
     AtomConvTcW tw{w.W2can, w.Mcan, w.W2Tcan};
     a.uv = e->uv[l].p;
-    launch_atomconv_bwd_tc(e->st, a, tw, e->num_sms);
+    if (e->ac_gen >= 3 && e->ac_gen != 4)  // B2M_ATOMCONV=4: third-generation forward with the first-generation backward
+      launch_atomconv_bwd_v3(e->st, a, tw, e->num_sms);
+    else
+      launch_atomconv_bwd_tc(e->st, a, tw, e->num_sms);
   } else {
     launch_atomconv_bwd(e->st, a);
   }
@@ -871,7 +875,7 @@ int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_han
       const char* leg = getenv("B2M_LEGACY_FFMA");
       e->use_tc = !(leg && leg[0] == '1');
       const char* gen = getenv("B2M_ATOMCONV");
-      e->ac_gen = gen ? atoi(gen) : 1;
+      e->ac_gen = gen ? atoi(gen) : 3;
     }
     B2M_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     for (auto& ev : e->ev) B2M_CK(cudaEventCreate(&ev));

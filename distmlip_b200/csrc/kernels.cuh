@@ -154,6 +154,7 @@ void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
 // third generation (kernels_ac3.cu): cp.async-staged gathers one tile ahead, no saved pre-activations unless uv_save
 void launch_atomconv_fwd_v3(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
+void launch_atomconv_bwd_v3(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms);
 // C[M,N] = (R | accum C | 0) + A[M,K] @ B + bias, B given as canonical hi/lo planes of its [N][K] view.
 // (K,N) in {(64,128), (64,64), (128,64)}.
 void launch_gemm_tc(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M, int N,

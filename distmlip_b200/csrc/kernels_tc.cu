@@ -670,635 +670,6 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
 }
 
-// ============================================================================================
-// atom conv forward, second generation (opt-in: B2M_ATOMCONV_V2=1).  Written after the round's GPU budget was spent:
-// it compiles for sm_100a but has NOT run on a GPU yet, so it is off by default (tests/test_gpu_experimental.py is
-// the A/B gate).  Differences to k_atomconv_fwd_tc, all aimed at the gather latency the profiles show
-// (profiles/r01c_stalls_by_source_line.txt: 44 % long-scoreboard, LSU 61 % busy with 16-byte-per-lane gathers):
-//   * one 512-thread CTA per SM = two independent 256-thread row groups (named barriers, 256 TMEM columns each)
-//     sharing ONE copy of the weights in shared memory (as the line-graph kernels do): 80 KB freed per SM
-//   * the gathered rows A[src] are brought in by the bulk-copy engine (cp.async.bulk, one 256-byte half row per edge
-//     and branch, completion on an mbarrier) into a padded [128][68] stage instead of per-lane LDG.128: no L1
-//     wavefront per lane, and the copy of the NEXT tile's first half is issued right after the current tile's
-//     second half has been consumed, i.e. it flies during GEMM2, the gate product, the u|v store and the segmented sum
-//   * the indices of the next tile are loaded one tile ahead (double-buffered), because its gathers need them early
-// Everything else (TMEM operand flow, 3xTF32, epilogues, saved tensors, segmented sum) is the first generation's.
-// ============================================================================================
-struct FwdV2Smem {
-  static constexpr int kBar = 0;                  // 2 groups x 4 mbarriers (3 MMA + 1 gather), tmem ptr at +48
-  static constexpr int kW2 = 64;                  // 4 x 4096
-  static constexpr int kM = kW2 + 4 * 4096;       // 2 x 2048
-  static constexpr int kWab = kM + 2 * 2048;      // 576, k-major [9][64]
-  static constexpr int kB2 = kWab + 576;          // 128
-  static constexpr int kGrp = kB2 + 128;          // per group:
-  static constexpr int kStagePitch = 68;          //   stage [128][68]  (gathered half rows, 272 B pitch)
-  static constexpr int kMsgOff = 128 * 68;        //   msg   [64][65]
-  static constexpr int kIdxOff = kMsgOff + 64 * 65;  // idx [2][3][128] ints (double-buffered src | dst | bond)
-  static constexpr int kGrpSize = kIdxOff + 2 * 3 * 128;
-  static constexpr int kTotal = kGrp + 2 * kGrpSize;
-  static constexpr size_t bytes = (size_t)kTotal * 4;
-};
-
-__global__ void __launch_bounds__(512, 1) k_atomconv_fwd_v2(const AtomConvArgs a, const AtomConvTcW w) {
-  extern __shared__ __align__(1024) float smem[];
-  const int tid = threadIdx.x;
-  const int g = tid >> 8, gt = tid & 255;
-  const int warp = gt >> 5, lane = tid & 31;
-  const int q = warp & 3, half = warp >> 2;
-  const int r = q * 32 + lane;  // my row (TMEM lane)
-  const int c0 = half * 32;     // my columns inside each 64-wide branch
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + FwdV2Smem::kBar) + g * 4;  // [0..2] MMA, [3] gather
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + FwdV2Smem::kBar + 48);
-  float* W2s = smem + FwdV2Smem::kW2;
-  float* Ms = smem + FwdV2Smem::kM;
-  float* wabW = smem + FwdV2Smem::kWab;
-  float* b2s = smem + FwdV2Smem::kB2;
-  float* grp = smem + FwdV2Smem::kGrp + g * FwdV2Smem::kGrpSize;
-  float* stage = grp;
-  float* msg = grp + FwdV2Smem::kMsgOff;
-  int* idx = reinterpret_cast<int*>(grp + FwdV2Smem::kIdxOff);  // [buf][src|dst|bond][128]
-  constexpr int PITCH = FwdV2Smem::kStagePitch;
-  const bool useQ = a.Qproj != nullptr;
-
-  if ((tid >> 5) == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(512u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (gt == 0) {
-    for (int i = 0; i < 4; i++) mbar_init_(&mbar[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < 4 * 1024; i += 512) reinterpret_cast<float4*>(W2s)[i] = reinterpret_cast<const float4*>(w.W2can)[i];
-  for (int i = tid; i < 2 * 512; i += 512) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
-  for (int i = tid; i < 576; i += 512) wabW[(i % 9) * 64 + i / 9] = a.Wabw[i];
-  if (tid < 128) b2s[tid] = a.b2[tid];
-
-  const int64_t ntiles = (a.E + 127) / 128;
-  const int64_t tstride = 2 * (int64_t)gridDim.x;
-  const int64_t t_first = 2 * (int64_t)blockIdx.x + g;
-  // indices of a tile into one of the two index buffers (rows past the end: src 0, dst/bond -1)
-  auto load_idx = [&](int64_t t, int buf) {
-    if (gt < 128) {
-      int src = 0, dst = -1, bond = -1;
-      const int64_t e = t * 128 + gt;
-      if (e < a.E) {
-        src = a.e_src[e];
-        dst = a.e_dst[e];
-        bond = a.e_bond[e];
-      }
-      int* ib = idx + buf * 384;
-      ib[gt] = src;
-      ib[128 + gt] = dst;
-      ib[256 + gt] = bond;
-    }
-  };
-  // bulk gather of one 64-column half (br) of A[src] for every valid row of a tile into the stage
-  auto issue_gather = [&](int64_t t, int buf, int br) {
-    const int nv = (int)min((int64_t)128, a.E - t * 128);
-    if (gt == 0) mbar_expect_tx_(&mbar[3], (uint32_t)nv * 256u);
-    if (gt < nv) bulk_g2s_(stage + gt * PITCH, a.Aproj + (size_t)idx[buf * 384 + gt] * D2 + br * 64, 256u, &mbar[3]);
-  };
-  if (t_first < ntiles) load_idx(t_first, 0);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tbase = *tptr + (uint32_t)g * 256u;
-  const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-  constexpr uint32_t COL_H = 0, COL_D = 128;
-  const uint32_t w2_addr = s_u32(W2s), m_addr = s_u32(Ms);
-  uint32_t phase = 0;   // parity of the three MMA barriers (one completion each per tile)
-  uint32_t gphase = 0;  // parity of the gather barrier (two completions per tile)
-  if (t_first < ntiles) issue_gather(t_first, 0, 0);
-
-  int buf = 0;
-  for (int64_t t = t_first; t < ntiles; t += tstride, buf ^= 1) {
-    const int64_t e0 = t * 128;
-    const int nvalid = (int)min((int64_t)128, a.E - e0);
-    const int64_t tn = t + tstride;
-    const bool have_next = tn < ntiles;
-    const int* s_src = idx + buf * 384;
-    const int* s_dst = s_src + 128;
-    const int* s_bond = s_src + 256;
-    // indices of my next tile: requested now, parked in registers, written to the other index buffer at the end of the
-    // first branch (so the load latency never blocks a warp); its gathers are issued at the end of the second branch
-    int nsrc = 0, ndst = -1, nbond = -1;
-    if (have_next && gt < 128) {
-      const int64_t e = tn * 128 + gt;
-      if (e < a.E) {
-        nsrc = a.e_src[e];
-        ndst = a.e_dst[e];
-        nbond = a.e_bond[e];
-      }
-    }
-    float bek[9];
-    {
-      const float4* bp = reinterpret_cast<const float4*>(a.be);
-      const float4 b0 = bp[tl4<3>(t, r, 0)], b1 = bp[tl4<3>(t, r, 4)], b2 = bp[tl4<3>(t, r, 8)];
-      bek[0] = b0.x, bek[1] = b0.y, bek[2] = b0.z, bek[3] = b0.w, bek[4] = b1.x, bek[5] = b1.y, bek[6] = b1.z,
-      bek[7] = b1.w, bek[8] = b2.x;
-      if (r >= nvalid) {
-#pragma unroll
-        for (int k = 0; k < 9; k++) bek[k] = 0.f;
-      }
-    }
-    if (half == 0) {
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const float x = k < 9 ? bek[k] : 0.f;
-        const uint32_t h = tf32_hi_bits(x);
-        hi[k] = h;
-        lo[k] = __float_as_uint(x - __uint_as_float(h));
-      }
-      tmem_st16(tlane + COL_H, hi);
-      tmem_st16(tlane + COL_H + 16, lo);
-    }
-    tc_wait_st();
-    tc_fence_before();
-    gbar(g);
-    if (gt == 0) {  // GEMM1: D[128 x 128] = be[128 x 16] . M^T
-      tc_fence_after();
-      uint32_t acc = 0;
-#pragma unroll
-      for (int term = 0; term < 3; term++) {
-        const uint32_t acol = term == 1 ? 16u : 0u;
-        const uint32_t bsel = m_addr + (term == 2 ? 2048u * 4u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < 2; ks++) {
-          umma_ts(tbase + COL_D, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 4096u, 2048u, 128u), kIdescN128, acc);
-          acc = 1;
-        }
-      }
-      umma_commit(&mbar[0]);
-    }
-    const int dst = s_dst[r], bond = s_bond[r];
-    const bool valid = r < nvalid;
-    const bool viaQ = useQ && bond >= 0;
-    const float* Crow = a.Cproj + (size_t)(valid ? dst : 0) * D2;
-    const float* Qrow = viaQ ? a.Qproj + (size_t)bond * D2 : nullptr;
-    const float* Astage = stage + r * PITCH + c0;  // my 32 columns of the staged half row
-#pragma unroll 1
-    for (int br = 0; br < 2; br++) {
-      mbar_wait_(&mbar[br], phase);   // GEMM1 (br 0) / GEMM2 of branch 0 (br 1: H is free again)
-      tc_fence_after();
-      mbar_wait_(&mbar[3], gphase);   // the staged half rows of this branch have landed
-      gphase ^= 1;
-      const int cb = br * 64 + c0;
-#pragma unroll
-      for (int ch = 0; ch < 2; ch++) {
-        uint32_t v[16], hi[16], lo[16];
-        tmem_ld16(tlane + COL_D + cb + ch * 16, v);
-        tc_wait_ld();
-        float av[16], cv[16];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float4 x = *reinterpret_cast<const float4*>(Astage + ch * 16 + i * 4);
-          const float4 y = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
-          av[4 * i] = x.x, av[4 * i + 1] = x.y, av[4 * i + 2] = x.z, av[4 * i + 3] = x.w;
-          cv[4 * i] = y.x, cv[4 * i + 1] = y.y, cv[4 * i + 2] = y.z, cv[4 * i + 3] = y.w;
-        }
-        if (viaQ) {
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const float4 x = *reinterpret_cast<const float4*>(Qrow + cb + ch * 16 + i * 4);
-            v[4 * i] = __float_as_uint(x.x), v[4 * i + 1] = __float_as_uint(x.y);
-            v[4 * i + 2] = __float_as_uint(x.z), v[4 * i + 3] = __float_as_uint(x.w);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const float p = __uint_as_float(v[i]) + av[i] + cv[i];
-          const float hval = valid ? silu_(p) : 0.f;
-          const uint32_t h = tf32_hi_bits(hval);
-          hi[i] = h;
-          lo[i] = __float_as_uint(hval - __uint_as_float(h));
-        }
-        tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
-        tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
-      }
-      if (br == 0 && have_next && gt < 128) {
-        int* ib = idx + (buf ^ 1) * 384;
-        ib[gt] = nsrc;
-        ib[128 + gt] = ndst;
-        ib[256 + gt] = nbond;
-      }
-      tc_wait_st();
-      tc_fence_before();
-      gbar(g);  // every thread of the group is done with H stores AND with reading the stage
-      if (gt == 0) {
-        tc_fence_after();
-        uint32_t acc = 0;
-#pragma unroll
-        for (int term = 0; term < 3; term++) {
-          const uint32_t acol = term == 1 ? 64u : 0u;
-          const uint32_t bsel = w2_addr + (uint32_t)(br * 2 + (term == 2 ? 1 : 0)) * 4096u * 4u;
-#pragma unroll
-          for (int ks = 0; ks < 8; ks++) {
-            umma_ts(tbase + COL_D + br * 64, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 2048u, 1024u, 128u),
-                    kIdescN64, acc);
-            acc = 1;
-          }
-        }
-        umma_commit(&mbar[br + 1]);
-      }
-      // refill the stage: the other half of this tile, or the first half of my next tile (generic-proxy reads of the
-      // stage are ordered before the async-proxy writes by the barrier above plus this proxy fence)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (br == 0)
-        issue_gather(t, buf, 1);
-      else if (have_next)
-        issue_gather(tn, buf ^ 1, 0);
-    }
-    mbar_wait_(&mbar[2], phase);
-    tc_fence_after();
-    phase ^= 1;
-    float mv[32];
-#pragma unroll
-    for (int ch = 0; ch < 2; ch++) {
-      uint32_t u[16], gg[16];
-      tmem_ld16(tlane + COL_D + c0 + ch * 16, u);
-      tmem_ld16(tlane + COL_D + 64 + c0 + ch * 16, gg);
-      float wab[16];
-      radial_dot16(wabW, c0 + ch * 16, bek, wab);
-      tc_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const int c = c0 + ch * 16 + i;
-        const float uu = __uint_as_float(u[i]) + b2s[c], vv = __uint_as_float(gg[i]) + b2s[64 + c];
-        u[i] = __float_as_uint(uu);
-        gg[i] = __float_as_uint(vv);
-        mv[ch * 16 + i] = valid ? silu_(uu) * sigm_(vv) * wab[i] : 0.f;
-      }
-      if (a.uv_save != nullptr && valid) {
-        float4* puv = reinterpret_cast<float4*>(a.uv_save);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          puv[tl4<32>(t, r, c0 + ch * 16 + 4 * i)] = make_float4(__uint_as_float(u[4 * i]), __uint_as_float(u[4 * i + 1]),
-                                                                __uint_as_float(u[4 * i + 2]), __uint_as_float(u[4 * i + 3]));
-          puv[tl4<32>(t, r, 64 + c0 + ch * 16 + 4 * i)] = make_float4(__uint_as_float(gg[4 * i]), __uint_as_float(gg[4 * i + 1]),
-                                                                     __uint_as_float(gg[4 * i + 2]), __uint_as_float(gg[4 * i + 3]));
-        }
-      }
-    }
-    tc_fence_before();
-#pragma unroll 1
-    for (int hp = 0; hp < 2; hp++) {
-      if ((q >> 1) == hp) {
-        const int rr = r - hp * 64;
-#pragma unroll
-        for (int i = 0; i < 32; i++) msg[rr * 65 + c0 + i] = mv[i];
-      }
-      gbar(g);
-      {
-        const int c = gt & 63, part = gt >> 6;  // 4 parts x 16 rows
-        float sum = 0.f;
-        int cur = -1;
-        const int rbeg = part * 16;
-        for (int rr = rbeg; rr < rbeg + 16; rr++) {
-          const int k = s_dst[hp * 64 + rr];
-          if (k != cur) {
-            if (cur >= 0) atomicAdd(&a.agg[(size_t)cur * D + c], sum);
-            cur = k;
-            sum = 0.f;
-          }
-          if (k >= 0) sum += msg[rr * 65 + c];
-        }
-        if (cur >= 0) atomicAdd(&a.agg[(size_t)cur * D + c], sum);
-      }
-      gbar(g);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if ((tid >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tptr), "r"(512u));
-}
-
-// second generation of the atom-conv backward (same opt-in switch and same caveat as k_atomconv_fwd_v2: compiled, not
-// yet run on a GPU): two row groups per CTA sharing the weights, bulk-copy gathers of the A[src] half rows one stage
-// ahead, next-tile indices one tile ahead.  The arithmetic is the first generation's, statement by statement.
-struct BwdV2Smem {
-  static constexpr int kBar = 0;                   // 2 groups x 4 mbarriers, tmem ptr at +48
-  static constexpr int kW2T = 64;                  // 4 x 4096
-  static constexpr int kM = kW2T + 4 * 4096;       // 2 x 2048 (canonical)
-  static constexpr int kMrow = kM + 2 * 2048;      // [128][12]
-  static constexpr int kWab = kMrow + 128 * 12;    // 576, k-major [9][64]
-  static constexpr int kGrp = kWab + 576;          // per group:
-  static constexpr int kStagePitch = 68;           //   stage [128][68]  gathered half rows of A
-  static constexpr int kSctOff = 128 * 68;         //   sct   [64][65]   scatter staging
-  static constexpr int kIdxOff = kSctOff + 64 * 65;   // idx [2][3][128]
-  static constexpr int kGrpSize = kIdxOff + 2 * 3 * 128;
-  static constexpr int kTotal = kGrp + 2 * kGrpSize;
-  static constexpr size_t bytes = (size_t)kTotal * 4;
-};
-
-__global__ void __launch_bounds__(512, 1) k_atomconv_bwd_v2(const AtomConvArgs a, const AtomConvTcW w) {
-  extern __shared__ __align__(1024) float smem[];
-  const int tid = threadIdx.x;
-  const int g = tid >> 8, gt = tid & 255;
-  const int warp = gt >> 5, lane = tid & 31;
-  const int q = warp & 3, half = warp >> 2;
-  const int r = q * 32 + lane;
-  const int c0 = half * 32;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + BwdV2Smem::kBar) + g * 4;  // [0..2] MMA, [3] gather
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(smem + BwdV2Smem::kBar + 48);
-  float* W2Ts = smem + BwdV2Smem::kW2T;
-  float* Ms = smem + BwdV2Smem::kM;
-  float* Mrow = smem + BwdV2Smem::kMrow;
-  float* wabW = smem + BwdV2Smem::kWab;
-  float* grp = smem + BwdV2Smem::kGrp + g * BwdV2Smem::kGrpSize;
-  float* stage = grp;
-  float* sct = grp + BwdV2Smem::kSctOff;
-  int* idx = reinterpret_cast<int*>(grp + BwdV2Smem::kIdxOff);
-  constexpr int PITCH = BwdV2Smem::kStagePitch;
-  const bool useQ = a.Qproj != nullptr;
-  const bool need_gx = a.gA != nullptr;
-
-  if ((tid >> 5) == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tptr)), "r"(512u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (gt == 0) {
-    for (int i = 0; i < 4; i++) mbar_init_(&mbar[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < 4 * 1024; i += 512) reinterpret_cast<float4*>(W2Ts)[i] = reinterpret_cast<const float4*>(w.W2Tcan)[i];
-  for (int i = tid; i < 2 * 512; i += 512) reinterpret_cast<float4*>(Ms)[i] = reinterpret_cast<const float4*>(w.Mcan)[i];
-  for (int i = tid; i < 576; i += 512) wabW[(i % 9) * 64 + i / 9] = a.Wabw[i];
-  for (int i = tid; i < 128 * 12; i += 512) Mrow[i] = (i % 12) < 9 ? a.M[(i / 12) * 9 + i % 12] : 0.f;
-
-  const int64_t ntiles = (a.E + 127) / 128;
-  const int64_t tstride = 2 * (int64_t)gridDim.x;
-  const int64_t t_first = 2 * (int64_t)blockIdx.x + g;
-  auto issue_gather = [&](int64_t t, int buf, int br) {
-    const int nv = (int)min((int64_t)128, a.E - t * 128);
-    if (gt == 0) mbar_expect_tx_(&mbar[3], (uint32_t)nv * 256u);
-    if (gt < nv) bulk_g2s_(stage + gt * PITCH, a.Aproj + (size_t)idx[buf * 384 + gt] * D2 + br * 64, 256u, &mbar[3]);
-  };
-  if (t_first < ntiles && gt < 128) {
-    int src = 0, dst = -1, bond = -1;
-    const int64_t e = t_first * 128 + gt;
-    if (e < a.E) {
-      src = a.e_src[e];
-      dst = a.e_dst[e];
-      bond = a.e_bond[e];
-    }
-    idx[gt] = src;
-    idx[128 + gt] = dst;
-    idx[256 + gt] = bond;
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tbase = *tptr + (uint32_t)g * 256u;
-  const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-  constexpr uint32_t COL_H = 0, COL_D = 128;
-  const uint32_t w2t_addr = s_u32(W2Ts), m_addr = s_u32(Ms);
-  uint32_t phase = 0, gphase = 0;
-  if (t_first < ntiles) issue_gather(t_first, 0, 0);
-
-  int buf = 0;
-  for (int64_t t = t_first; t < ntiles; t += tstride, buf ^= 1) {
-    const int64_t e0 = t * 128;
-    const int nvalid = (int)min((int64_t)128, a.E - e0);
-    const int64_t tn = t + tstride;
-    const bool have_next = tn < ntiles;
-    const int* s_src = idx + buf * 384;
-    const int* s_dst = s_src + 128;
-    const int* s_bond = s_src + 256;
-    int nsrc = 0, ndst = -1, nbond = -1;  // indices of my next tile, parked in registers until the end of branch 0
-    if (have_next && gt < 128) {
-      const int64_t e = tn * 128 + gt;
-      if (e < a.E) {
-        nsrc = a.e_src[e];
-        ndst = a.e_dst[e];
-        nbond = a.e_bond[e];
-      }
-    }
-    float bek[9], dbek[9];
-    {
-      const float4* bp = reinterpret_cast<const float4*>(a.be);
-      const float4* dp4 = reinterpret_cast<const float4*>(a.dbe);
-      const float4 b0 = bp[tl4<3>(t, r, 0)], b1 = bp[tl4<3>(t, r, 4)], b2 = bp[tl4<3>(t, r, 8)];
-      const float4 d0 = dp4[tl4<3>(t, r, 0)], d1 = dp4[tl4<3>(t, r, 4)], d2 = dp4[tl4<3>(t, r, 8)];
-      bek[0] = b0.x, bek[1] = b0.y, bek[2] = b0.z, bek[3] = b0.w, bek[4] = b1.x, bek[5] = b1.y, bek[6] = b1.z,
-      bek[7] = b1.w, bek[8] = b2.x;
-      dbek[0] = d0.x, dbek[1] = d0.y, dbek[2] = d0.z, dbek[3] = d0.w, dbek[4] = d1.x, dbek[5] = d1.y, dbek[6] = d1.z,
-      dbek[7] = d1.w, dbek[8] = d2.x;
-      if (r >= nvalid) {
-#pragma unroll
-        for (int k = 0; k < 9; k++) bek[k] = dbek[k] = 0.f;
-      }
-    }
-    if (half == 0) {
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const float x = k < 9 ? bek[k] : 0.f;
-        const uint32_t h = tf32_hi_bits(x);
-        hi[k] = h;
-        lo[k] = __float_as_uint(x - __uint_as_float(h));
-      }
-      tmem_st16(tlane + COL_H, hi);
-      tmem_st16(tlane + COL_H + 16, lo);
-    }
-    tc_wait_st();
-    tc_fence_before();
-    gbar(g);
-    if (gt == 0) {
-      tc_fence_after();
-      uint32_t acc = 0;
-#pragma unroll
-      for (int term = 0; term < 3; term++) {
-        const uint32_t acol = term == 1 ? 16u : 0u;
-        const uint32_t bsel = m_addr + (term == 2 ? 2048u * 4u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < 2; ks++) {
-          umma_ts(tbase + COL_D, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 4096u, 2048u, 128u), kIdescN128, acc);
-          acc = 1;
-        }
-      }
-      umma_commit(&mbar[0]);
-    }
-    const int dst = s_dst[r], bond = s_bond[r];
-    const bool valid = r < nvalid;
-    const bool viaQ = useQ && bond >= 0;
-    const float* Astage = stage + r * PITCH + c0;
-    const float* Crow = a.Cproj + (size_t)(valid ? dst : 0) * D2;
-    const float* Qrow = viaQ ? a.Qproj + (size_t)bond * D2 : nullptr;
-    const float4* uv4 = reinterpret_cast<const float4*>(a.uv);
-    const float* gmrow = a.gagg + (size_t)(valid ? dst : 0) * D;
-    float gdpart = 0.f;
-    float gbeM[12];
-#pragma unroll
-    for (int k = 0; k < 12; k++) gbeM[k] = 0.f;
-
-#pragma unroll 1
-    for (int br = 0; br < 2; br++) {
-      mbar_wait_(&mbar[br], phase);
-      tc_fence_after();
-      mbar_wait_(&mbar[3], gphase);  // staged half rows of A for this branch
-      gphase ^= 1;
-      const int cb = br * 64 + c0;
-      float ds[32];
-#pragma unroll
-      for (int ch = 0; ch < 2; ch++) {
-        uint32_t v[16], hi[16], lo[16];
-        tmem_ld16(tlane + COL_D + cb + ch * 16, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float4 x = *reinterpret_cast<const float4*>(Astage + ch * 16 + i * 4);
-          const float4 y = *reinterpret_cast<const float4*>(Crow + cb + ch * 16 + i * 4);
-          float4 t4 = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                  __uint_as_float(v[4 * i + 3]));
-          if (viaQ) t4 = *reinterpret_cast<const float4*>(Qrow + cb + ch * 16 + i * 4);
-          const float p0 = t4.x + x.x + y.x, p1 = t4.y + x.y + y.y, p2 = t4.z + x.z + y.z, p3 = t4.w + x.w + y.w;
-          float sg;
-          sg = sigm_(p0), ds[ch * 16 + 4 * i] = sg * (1.f + p0 * (1.f - sg));
-          sg = sigm_(p1), ds[ch * 16 + 4 * i + 1] = sg * (1.f + p1 * (1.f - sg));
-          sg = sigm_(p2), ds[ch * 16 + 4 * i + 2] = sg * (1.f + p2 * (1.f - sg));
-          sg = sigm_(p3), ds[ch * 16 + 4 * i + 3] = sg * (1.f + p3 * (1.f - sg));
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int c = c0 + ch * 16 + i * 4;
-          const float4 u4 = uv4[tl4<32>(t, r, c)];
-          const float4 v4 = uv4[tl4<32>(t, r, 64 + c)];
-          const float4 g4 = *reinterpret_cast<const float4*>(gmrow + c);
-          const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
-          float wab4[4], wabp4[4];
-          radial_dot4(wabW, c, bek, wab4);
-          if (br == 0) radial_dot4(wabW, c, dbek, wabp4);
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const float wab = wab4[j];
-            const float su = sigm_(uu[j]), oG = sigm_(vv[j]);
-            const float oL = uu[j] * su;
-            float gv;
-            if (br == 0) {
-              gv = gg[j] * oG * wab * (su * (1.f + uu[j] * (1.f - su)));
-              gdpart = fmaf(gg[j] * oL * oG, wabp4[j], gdpart);
-            } else {
-              gv = gg[j] * oL * wab * oG * (1.f - oG);
-            }
-            if (!valid) gv = 0.f;
-            const uint32_t h = tf32_hi_bits(gv);
-            hi[4 * i + j] = h;
-            lo[4 * i + j] = __float_as_uint(gv - __uint_as_float(h));
-          }
-        }
-        tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
-        tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
-      }
-      if (br == 0 && have_next && gt < 128) {
-        int* ib = idx + (buf ^ 1) * 384;
-        ib[gt] = nsrc;
-        ib[128 + gt] = ndst;
-        ib[256 + gt] = nbond;
-      }
-      tc_wait_st();
-      tc_fence_before();
-      gbar(g);  // H complete, stage consumed
-      if (gt == 0) {
-        tc_fence_after();
-        uint32_t acc = 0;
-#pragma unroll
-        for (int term = 0; term < 3; term++) {
-          const uint32_t acol = term == 1 ? 64u : 0u;
-          const uint32_t bsel = w2t_addr + (uint32_t)(br * 2 + (term == 2 ? 1 : 0)) * 4096u * 4u;
-#pragma unroll
-          for (int ks = 0; ks < 8; ks++) {
-            umma_ts(tbase + COL_D + br * 64, tbase + COL_H + acol + ks * 8, umma_desc(bsel + ks * 2048u, 1024u, 128u),
-                    kIdescN64, acc);
-            acc = 1;
-          }
-        }
-        umma_commit(&mbar[br + 1]);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (br == 0)
-        issue_gather(t, buf, 1);
-      else if (have_next)
-        issue_gather(tn, buf ^ 1, 0);
-      mbar_wait_(&mbar[br + 1], phase);
-      tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < 2; ch++) {
-        uint32_t v[16];
-        tmem_ld16(tlane + COL_D + br * 64 + c0 + ch * 16, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; i++) ds[ch * 16 + i] *= __uint_as_float(v[i]);
-      }
-      if (!viaQ) {
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const float4* Mj = reinterpret_cast<const float4*>(Mrow + (cb + i) * 12);
-#pragma unroll
-          for (int k4 = 0; k4 < 3; k4++) {
-            const float4 m = Mj[k4];
-            ffma2(gbeM[4 * k4], gbeM[4 * k4 + 1], ds[i], m.x, m.y);
-            ffma2(gbeM[4 * k4 + 2], gbeM[4 * k4 + 3], ds[i], m.z, m.w);
-          }
-        }
-      }
-      if (need_gx) {
-#pragma unroll 1
-        for (int hp = 0; hp < 2; hp++) {
-          if ((q >> 1) == hp) {
-            const int rr = r - hp * 64;
-#pragma unroll
-            for (int i = 0; i < 32; i++) sct[rr * 65 + c0 + i] = ds[i];
-          }
-          gbar(g);
-          {
-            const int c4 = gt & 15, part = gt >> 4;  // 16 parts x 4 rows
-            const int col = br * 64 + c4 * 4;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            int cur = -1;
-            const int rbeg = part * 4;
-            for (int rr = rbeg; rr < rbeg + 4; rr++) {
-              const int row = hp * 64 + rr;
-              const int k = s_dst[row];
-              const float v0 = sct[rr * 65 + c4 * 4], v1 = sct[rr * 65 + c4 * 4 + 1], v2 = sct[rr * 65 + c4 * 4 + 2],
-                          v3 = sct[rr * 65 + c4 * 4 + 3];
-              if (k != cur) {
-                if (cur >= 0) red_add_v4(&a.gC[(size_t)cur * D2 + col], s0, s1, s2, s3);
-                cur = k;
-                s0 = s1 = s2 = s3 = 0.f;
-              }
-              if (k >= 0) {
-                s0 += v0, s1 += v1, s2 += v2, s3 += v3;
-                red_add_v4(&a.gA[(size_t)s_src[row] * D2 + col], v0, v1, v2, v3);
-                const int bnd = s_bond[row];
-                if (useQ && bnd >= 0) *reinterpret_cast<float4*>(&a.gQ[(size_t)bnd * D2 + col]) = make_float4(v0, v1, v2, v3);
-              }
-            }
-            if (cur >= 0) red_add_v4(&a.gC[(size_t)cur * D2 + col], s0, s1, s2, s3);
-          }
-          gbar(g);
-        }
-      }
-    }
-    phase ^= 1;
-    {
-      float sacc = gdpart;
-#pragma unroll
-      for (int k = 0; k < 9; k++) sacc = fmaf(gbeM[k], dbek[k], sacc);
-      sct[gt] = valid ? sacc : 0.f;
-      tc_fence_before();
-      gbar(g);
-      if (gt < nvalid) a.gd[e0 + gt] += sct[gt] + sct[128 + gt];
-      gbar(g);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if ((tid >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tptr), "r"(512u));
-}
-
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
   static PerDeviceOnce attr;
@@ -1312,21 +683,6 @@ void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
     const char* v = getenv("B2M_BWD_THREADS");
     return (v && atoi(v) == 512) ? 512 : 256;  // 512 (4 threads/row, 64 regs) measured slower: LSU-bound, not warp-bound
   }();
-  static const bool v2 = [] {
-    const char* v = getenv("B2M_ATOMCONV_V2");
-    return v && atoi(v) != 0;
-  }();
-  if (v2) {
-    static PerDeviceOnce attr2;
-    if (attr2.first()) {
-      B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdV2Smem::bytes));
-    }
-    const int grid2 = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
-    k_atomconv_bwd_v2<<<grid2, 512, BwdV2Smem::bytes, st>>>(a, w);
-    B2M_CK(cudaGetLastError());
-    g_launch_count++;
-    return;
-  }
   AtomConvTcW wl = w;
   wl.l2pf = l2pf_level() >= 1;
   if (nthr == 512)
@@ -1356,21 +712,6 @@ void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomCo
     const char* v = getenv("B2M_FWD_PREFETCH");
     return v ? atoi(v) != 0 : kFwdPrefetchDefault;
   }();
-  static const bool v2 = [] {
-    const char* v = getenv("B2M_ATOMCONV_V2");
-    return v && atoi(v) != 0;
-  }();
-  if (v2) {
-    static PerDeviceOnce attr2;
-    if (attr2.first()) {
-      B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdV2Smem::bytes));
-    }
-    const int grid2 = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
-    k_atomconv_fwd_v2<<<grid2, 512, FwdV2Smem::bytes, st>>>(a, w);
-    B2M_CK(cudaGetLastError());
-    g_launch_count++;
-    return;
-  }
   AtomConvTcW wl = w;
   wl.l2pf = l2pf_level() >= 1;
   if (nthr == 512)

@@ -16,8 +16,9 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("B2M_TEST_EXPERIMENTAL") != "1", reason="opt-in: B2M_TEST_EXPERIMENTAL=1")]
 
 SWITCHES = [
-    {"B2M_ATOMCONV": "3"},
-    {"B2M_ATOMCONV_V2": "1"},
+    {"B2M_ATOMCONV": "1"},
+    {"B2M_ATOMCONV": "4"},
+    {"B2M_AC3_L1PF": "0"},
     {"B2M_GEMM_PIPE": "0"},
     {"B2M_L2_PREFETCH": "2"},
     {"B2M_L2_PREFETCH": "0"},
@@ -30,7 +31,7 @@ def _run(tmp_path, name, extra_env):
     out = tmp_path / f"{name}.npz"
     env = dict(os.environ, **extra_env)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_run_case.py"), str(out)], env=env, cwd=ROOT,
-                       capture_output=True, text=True, timeout=300)
+                       capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
     return np.load(out)
 
