@@ -88,7 +88,8 @@ def comm_unique_id() -> bytes:
 
 
 class Engine:
-    """Thin RAII wrapper over a b2m_handle (one GPU, one process)."""
+    """Thin RAII wrapper over a b2m_handle.  `device`: one CUDA ordinal (one partition, or one rank of a multi-process
+    job) or a list of ordinals = a single-process group with one partition per entry (ordinals may repeat)."""
 
     def __init__(self, *, n_elem, dim, max_n, max_f, n_blocks, cutoff, three_body_cutoff, cutoff_exponent,
                  data_mean=0.0, data_std=1.0, device=0):
@@ -96,12 +97,14 @@ class Engine:
         self.desc = ModelDesc(n_elem, dim, max_n, max_f, n_blocks, cutoff_exponent, cutoff, three_body_cutoff,
                               data_mean, data_std)
         self.h = C.c_void_p()
-        dev = (C.c_int * 1)(int(device))
-        rc = self.lib.b2m_create(C.byref(self.desc), dev, 1, C.byref(self.h))
+        devs = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        dev = (C.c_int * len(devs))(*devs)
+        rc = self.lib.b2m_create(C.byref(self.desc), dev, len(devs), C.byref(self.h))
         if rc != 0:
             raise B2MError(rc, (self.lib.b2m_last_error(None) or b"").decode())
         self.natoms = 0
-        self.rank, self.world = 0, 1
+        self.rank, self.world = 0, len(devs)
+        self.group = len(devs) > 1
 
     def _ck(self, rc):
         if rc != 0:

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -59,19 +61,30 @@ struct DBuf {
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: guards are per device so that a
-// second engine on another GPU of the same process sets them again.
+// second engine on another GPU of the same process sets them again.  The guard holds a lock until the end
+// of the `if` statement it is declared in: the partition threads of a single-process group may reach a launcher at
+// the same time, and the second one must not launch before the first has finished setting the attribute.
+//   if (auto once = attr.first(); once) { cudaFuncSetAttribute(...); }
 struct PerDeviceOnce {
+  std::mutex m;
   bool done[64] = {};
-  bool first() {
+  struct Guard {
+    std::unique_lock<std::mutex> lk;
+    bool need;
+    explicit operator bool() const { return need; }
+  };
+  Guard first() {
+    Guard g{std::unique_lock<std::mutex>(m), true};
     int d = 0;
-    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
-    if (done[d]) return false;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return g;
+    g.need = !done[d];
     done[d] = true;
-    return true;
+    return g;
   }
 };
 
-extern long long g_launch_count;  // kernels launched by this library (bench.py gpu_launches)
+extern std::atomic<long long> g_launch_count;  // kernels launched by this library (bench.py gpu_launches); atomic: the
+                                               // partitions of a single-process group are driven by one host thread each
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

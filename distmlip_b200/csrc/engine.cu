@@ -9,6 +9,9 @@
 #include <nccl.h>
 
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstring>
 #include <map>
 #include <set>
@@ -78,6 +81,34 @@ struct BondLayerW {
 
 using namespace b2m;
 
+// Host-side rendezvous of the partition threads of a single-process group (b2m_create with ndev > 1).  abort() releases
+// every waiter so that an exception in one partition cannot dead-lock the others.
+struct GroupSync {
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 1, waiting = 0;
+  long long gen = 0;
+  bool aborted = false;
+  void reset(int n_) { n = n_, waiting = 0, aborted = false; }
+  void arrive_and_wait() {
+    std::unique_lock<std::mutex> lk(m);
+    if (aborted) throw b2m::Error(B2M_ERR_STATE, "a partition of the group failed");
+    const long long my = gen;
+    if (++waiting == n) {
+      waiting = 0, gen++;
+      cv.notify_all();
+      return;
+    }
+    cv.wait(lk, [&] { return gen != my || aborted; });
+    if (aborted && gen == my) throw b2m::Error(B2M_ERR_STATE, "a partition of the group failed");
+  }
+  void abort() {
+    std::lock_guard<std::mutex> lk(m);
+    aborted = true;
+    cv.notify_all();
+  }
+};
+
 struct b2m_engine {
   b2m_model_desc desc;
   int device = 0;
@@ -102,6 +133,16 @@ struct b2m_engine {
   // comm
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
+  // single-process group (ndev > 1): the handle returned by b2m_create is parts[0]; every partition is a full engine on
+  // its own device (ordinals may repeat) and stream, driven by its own host thread inside b2m_set_structure /
+  // b2m_compute; halo rows travel as direct peer-memory stores / copies ordered by CUDA events (no NCCL)
+  std::vector<b2m_engine*> parts;  // leader only: all partitions, parts[0] == this
+  b2m_engine* leader = nullptr;    // members: the leader (for the peer table and the rendezvous)
+  GroupSync gsync;                 // leader only
+  std::vector<cudaEvent_t> hev;    // one event per halo-exchange point of a run
+  int hpoint = 0;
+  DBuf<float> precv[2];            // adjoint rows pushed by my neighbours (backward), double-buffered by point parity
+  DBuf<float> ftmp;                // leader: staging of a peer's force array
   // graph + workspace
   Graph g;
   bool have_graph = false;
@@ -489,22 +530,59 @@ static void alloc_workspace(b2m_engine* e) {
     size_t tot_to = 0, tot_bto = 0;
     for (int q = 0; q < e->world; q++) tot_to += g.n_to[q], tot_bto += g.nb_to[q];
     size_t m = std::max(tot_to * D, tot_bto * D);
-    e->sendbuf.ensure(m + 64);
-    e->recvbuf.ensure(m + 64);
+    if (e->leader != nullptr) {
+      e->precv[0].ensure(m + 64), e->precv[1].ensure(m + 64);
+    } else {
+      e->sendbuf.ensure(m + 64);
+      e->recvbuf.ensure(m + 64);
+    }
   }
 }
 
-// ---- halo exchange (NCCL p2p between slab neighbours) ----
-// forward: rows of `buf` listed in to_list[q] -> q's halo section; my halo section <- owners
-static void halo_forward(b2m_engine* e, float* buf, bool bonds) {
+// ---- halo exchange between slab neighbours ----
+// Two transports: NCCL point-to-point (one process per GPU, world > 1 with a communicator) and, inside a single-process
+// group, direct peer-memory traffic: the sender's pack kernel stores its boundary rows straight into the receiver's halo
+// rows (forward) or copies its halo adjoints into the owner's receive buffer (backward); a CUDA event per exchange point
+// orders the receiver's stream behind the sender's.
+static float* halo_buffer(b2m_engine* e, bool bonds, int l) { return bonds ? e->h[l].p : e->x[l].p; }
+
+static cudaEvent_t next_halo_event(b2m_engine* e) {
+  // the events are created in b2m_create: a neighbour's thread reads hev[k] concurrently, so the vector never grows here
+  B2M_REQUIRE(e->hpoint < (int)e->hev.size(), B2M_ERR_STATE, "too many halo-exchange points in one evaluation");
+  return e->hev[e->hpoint];
+}
+
+// forward: rows of tensor (bonds ? h : x)[l] listed in to_list[q] -> q's halo section; my halo section <- owners
+static void halo_forward(b2m_engine* e, bool bonds, int l) {
   if (e->world <= 1) return;
   Graph& g = e->g;
+  float* buf = halo_buffer(e, bonds, l);
   const int* nto = bonds ? g.nb_to : g.n_to;
   const int* toff = bonds ? g.bto_off : g.to_off;
   const int* nfrom = bonds ? g.nb_from : g.n_from;
   const int* foff = bonds ? g.bfrom_off : g.from_off;
   const int* list = bonds ? g.bto_list.p : g.to_list.p;
   const size_t base = bonds ? (size_t)g.B_own : (size_t)g.n_own;
+  if (e->leader != nullptr) {
+    b2m_engine* L = e->leader;
+    for (int q = 0; q < e->world; q++) {
+      if (q == e->rank || nto[q] <= 0) continue;
+      b2m_engine* pe = L->parts[q];
+      Graph& pg = pe->g;
+      const int pn = bonds ? pg.nb_from[e->rank] : pg.n_from[e->rank];
+      B2M_REQUIRE(pn == nto[q], B2M_ERR_STATE, "halo sections of two partitions disagree");
+      const size_t pbase = bonds ? (size_t)pg.B_own : (size_t)pg.n_own;
+      const size_t pfoff = bonds ? (size_t)pg.bfrom_off[e->rank] : (size_t)pg.from_off[e->rank];
+      launch_gather_rows(e->st, nto[q], D, list + toff[q], buf, halo_buffer(pe, bonds, l) + (pbase + pfoff) * D);
+    }
+    cudaEvent_t ev = next_halo_event(e);
+    B2M_CK(cudaEventRecord(ev, e->st));
+    const int k = e->hpoint++;
+    L->gsync.arrive_and_wait();  // every partition has recorded its event for this point
+    for (int q = 0; q < e->world; q++)  // (every partition records an event at every point: waiting on all is always valid)
+      if (q != e->rank) B2M_CK(cudaStreamWaitEvent(e->st, L->parts[q]->hev[k], 0));
+    return;
+  }
   for (int q = 0; q < e->world; q++)
     if (nto[q] > 0) launch_gather_rows(e->st, nto[q], D, list + toff[q], buf, e->sendbuf.p + (size_t)toff[q] * D);
   NCCL_CK(g_nccl.GroupStart());
@@ -528,6 +606,29 @@ static void halo_backward(b2m_engine* e, float* gbuf, bool bonds) {
   const int* list = bonds ? g.bto_list.p : g.to_list.p;
   const size_t base = bonds ? (size_t)g.B_own : (size_t)g.n_own;
   const size_t nhalo = bonds ? (size_t)g.B_halo : (size_t)g.n_halo;
+  if (e->leader != nullptr) {
+    b2m_engine* L = e->leader;
+    const int k = e->hpoint;
+    for (int q = 0; q < e->world; q++) {
+      if (q == e->rank || nfrom[q] <= 0) continue;
+      b2m_engine* pe = L->parts[q];
+      const size_t ptoff = bonds ? (size_t)pe->g.bto_off[e->rank] : (size_t)pe->g.to_off[e->rank];
+      // the owner's receive buffer of this parity was consumed two exchange points ago (group mode)
+      B2M_CK(cudaMemcpyAsync(pe->precv[k & 1].p + ptoff * D, gbuf + (base + foff[q]) * D, (size_t)nfrom[q] * D * sizeof(float),
+                             cudaMemcpyDefault, e->st));
+    }
+    launch_zero_rows(e->st, gbuf + base * D, nhalo * D);
+    cudaEvent_t ev = next_halo_event(e);
+    B2M_CK(cudaEventRecord(ev, e->st));
+    e->hpoint++;
+    L->gsync.arrive_and_wait();
+    for (int q = 0; q < e->world; q++)
+      if (q != e->rank) B2M_CK(cudaStreamWaitEvent(e->st, L->parts[q]->hev[k], 0));
+    for (int q = 0; q < e->world; q++)
+      if (q != e->rank && nto[q] > 0)
+        launch_scatter_add_rows(e->st, nto[q], D, list + toff[q], e->precv[k & 1].p + (size_t)toff[q] * D, gbuf);
+    return;
+  }
   NCCL_CK(g_nccl.GroupStart());
   for (int q = 0; q < e->world; q++) {
     if (q == e->rank) continue;
@@ -694,7 +795,7 @@ static void forward(b2m_engine* e) {
   launch_angle_init(e->st, g.A, g.a_in.p, g.a_out.p, g.b_vec.p, e->d_fa, e->d_Wae, e->ang[0].p);
   for (int l = 0; l < nb - 1; l++) {
     atom_layer_fwd(e, l);
-    halo_forward(e, e->x[l + 1].p, false);
+    halo_forward(e, false, l + 1);
     const BondLayerW& w = e->bw[l];
     line_projections(e, l, true);
     launch_zero_rows(e->st, e->aggB.p, (int64_t)g.B_own * D);
@@ -706,7 +807,7 @@ static void forward(b2m_engine* e) {
     if (l < nb - 2) {
       // the last block's angle update (and the halo copy of h feeding it) is dead code in the
       // reference (chgnet.py:353-368 on the last iteration): nothing reads it afterwards.
-      halo_forward(e, e->h[l + 1].p, true);
+      halo_forward(e, true, l + 1);
       line_projections(e, l, false);
       LineArgs b = line_args(e, l, false);
       b.ang_out = e->ang[l + 1].p;
@@ -773,8 +874,9 @@ static void backward(b2m_engine* e) {
 static void run(b2m_engine* e, bool grads) {
   B2M_REQUIRE(e->finalized, B2M_ERR_STATE, "weights not finalized");
   B2M_REQUIRE(e->have_graph, B2M_ERR_STATE, "b2m_set_structure has not been called");
-  B2M_REQUIRE(e->world == 1 || e->comm != nullptr, B2M_ERR_STATE,
+  B2M_REQUIRE(e->world == 1 || e->comm != nullptr || e->leader != nullptr, B2M_ERR_STATE,
               "world > 1 without a communicator (b2m_set_partition is a graph-only view)");
+  e->hpoint = 0;
   for (auto& p : e->gather_ev) {
     cudaEventDestroy(p.first);
     cudaEventDestroy(p.second);
@@ -786,7 +888,7 @@ static void run(b2m_engine* e, bool grads) {
   forward(e);
   B2M_CK(cudaEventRecord(e->ev[1], e->st));
   if (grads) backward(e);
-  if (e->world > 1) {
+  if (e->world > 1 && e->leader == nullptr) {
     NCCL_CK(g_nccl.AllReduce(e->scal.p, e->scal.p, 10, ncclFloat64, ncclSum, e->comm, e->st));
     if (grads)
       NCCL_CK(g_nccl.AllReduce(e->forces.p, e->forces.p, (size_t)e->g.N * 3, ncclFloat32, ncclSum, e->comm, e->st));
@@ -808,12 +910,81 @@ static void run(b2m_engine* e, bool grads) {
   e->t_total = e->t_fwd + e->t_bwd;
 }
 
+__global__ void k_add_inplace(int64_t n, const float* __restrict__ src, float* __restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+// Runs fn(partition) for every partition of a group, one host thread each (each sets its own device); the first
+// exception wins and releases the others from the rendezvous.
+template <class F>
+static void for_each_part(b2m_engine* L, F fn) {
+  const int n = (int)L->parts.size();
+  L->gsync.reset(n);
+  std::vector<std::string> errs(n);
+  std::vector<int> codes(n, 0);
+  std::vector<std::thread> th;
+  for (int p = 0; p < n; p++)
+    th.emplace_back([&, p] {
+      try {
+        B2M_CK(cudaSetDevice(L->parts[p]->device));
+        fn(L->parts[p]);
+      } catch (const b2m::Error& ex) {
+        codes[p] = ex.code, errs[p] = ex.what();
+        L->gsync.abort();
+      } catch (const std::exception& ex) {
+        codes[p] = B2M_ERR_INVALID, errs[p] = ex.what();
+        L->gsync.abort();
+      }
+    });
+  for (auto& t : th) t.join();
+  cudaSetDevice(L->device);
+  for (int p = 0; p < n; p++)
+    if (codes[p] != 0 && errs[p].find("a partition of the group failed") == std::string::npos)
+      throw Error(codes[p], "partition " + std::to_string(p) + ": " + errs[p]);
+  for (int p = 0; p < n; p++)
+    if (codes[p] != 0) throw Error(codes[p], errs[p]);
+}
+
+static void run_any(b2m_engine* e, bool grads) {
+  if (e->parts.empty()) {
+    run(e, grads);
+    return;
+  }
+  for_each_part(e, [&](b2m_engine* pe) { run(pe, grads); });
+  // slowest partition = the group's device time; launches summed
+  long long launches = 0;
+  for (auto* pe : e->parts) {
+    e->t_fwd = std::max(e->t_fwd, pe->t_fwd), e->t_bwd = std::max(e->t_bwd, pe->t_bwd);
+    e->t_total = std::max(e->t_total, pe->t_total);
+    launches += pe->launches_last;
+  }
+  e->launches_last = launches;
+}
+
 static void fetch(b2m_engine* e, double* energy, float* forces, float* stress9) {
   double hs[10];
   B2M_CK(cudaMemcpyAsync(hs, e->scal.p, 10 * sizeof(double), cudaMemcpyDeviceToHost, e->st));
+  if (!e->parts.empty() && forces) {  // group: sum the partitions' force arrays on the leader's device
+    const size_t n = (size_t)e->g.N * 3;
+    e->ftmp.ensure(n + 64);
+    for (size_t p = 1; p < e->parts.size(); p++) {
+      B2M_CK(cudaMemcpyAsync(e->ftmp.p, e->parts[p]->forces.p, n * sizeof(float), cudaMemcpyDefault, e->st));
+      k_add_inplace<<<cdiv((int64_t)n, 256), 256, 0, e->st>>>((int64_t)n, e->ftmp.p, e->forces.p);
+      B2M_CK(cudaGetLastError());
+    }
+  }
   if (forces)
     B2M_CK(cudaMemcpyAsync(forces, e->forces.p, (size_t)e->g.N * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
   B2M_CK(cudaStreamSynchronize(e->st));
+  for (size_t p = 1; p < e->parts.size(); p++) {  // energy and virial of the other partitions
+    double ps[10];
+    b2m_engine* pe = e->parts[p];
+    B2M_CK(cudaSetDevice(pe->device));
+    B2M_CK(cudaMemcpy(ps, pe->scal.p, 10 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 10; k++) hs[k] += ps[k];
+  }
+  if (!e->parts.empty()) B2M_CK(cudaSetDevice(e->device));
   e->last_energy = hs[0] + e->desc.data_mean;
   if (energy) *energy = e->last_energy;
   if (stress9)
@@ -843,12 +1014,52 @@ static void fetch(b2m_engine* e, double* energy, float* forces, float* stress9) 
 
 static std::string g_create_err;
 
+// every partition of a single-process group holds the replicated weights (chgnet.py:455-549 deep-copies them per GPU)
+template <class F>
+static void each_member(b2m_engine* h, F fn) {
+  if (h->parts.empty()) {
+    fn(h);
+    return;
+  }
+  for (auto* pe : h->parts) {
+    B2M_CK(cudaSetDevice(pe->device));
+    fn(pe);
+  }
+  B2M_CK(cudaSetDevice(h->device));
+}
+
+
 extern "C" {
+
+static b2m_engine* create_one(const b2m_model_desc* desc, int device, int count) {
+  B2M_REQUIRE(device >= 0 && device < count, B2M_ERR_INVALID, "bad device ordinal");
+  b2m_engine* e = new b2m_engine();
+  try {
+    e->desc = *desc;
+    e->device = device;
+    B2M_CK(cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    B2M_CK(cudaGetDeviceProperties(&prop, e->device));
+    if (prop.major != 10) throw Error(B2M_ERR_CUDA, "libb200mlip is built for sm_100a (B200) only");
+    e->num_sms = prop.multiProcessorCount;
+    const char* leg = getenv("B2M_LEGACY_FFMA");
+    e->use_tc = !(leg && leg[0] == '1');
+    const char* gen = getenv("B2M_ATOMCONV");
+    e->ac_gen = gen ? atoi(gen) : 3;
+    B2M_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    for (auto& ev : e->ev) B2M_CK(cudaEventCreate(&ev));
+  } catch (...) {
+    delete e;
+    throw;
+  }
+  return e;
+}
 
 int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_handle* out) {
   if (!desc || !devices || !out) return B2M_ERR_INVALID;
+  std::vector<b2m_engine*> made;
   try {
-    B2M_REQUIRE(ndev == 1, B2M_ERR_INVALID, "one process per GPU: ndev must be 1 (use b2m_comm_init for world > 1)");
+    B2M_REQUIRE(ndev >= 1 && ndev <= MAXP, B2M_ERR_PARTITIONS, "ndev must be in [1,16]");
     B2M_REQUIRE(desc->dim == D && desc->max_n == NR && desc->max_f == 4, B2M_ERR_INVALID,
                 "engine supports dim=64, max_n=9, max_f=4");
     B2M_REQUIRE(desc->n_blocks >= 2 && desc->n_blocks <= 16, B2M_ERR_INVALID, "n_blocks must be in [2,16]");
@@ -859,36 +1070,39 @@ int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_han
     if (ce != cudaSuccess || count <= 0)
       throw Error(B2M_ERR_CUDA, std::string("no CUDA device available (libb200mlip has no CPU fallback): ") +
                                     cudaGetErrorString(ce));
-    B2M_REQUIRE(devices[0] >= 0 && devices[0] < count, B2M_ERR_INVALID, "bad device ordinal");
-    b2m_engine* e = new b2m_engine();
-    e->desc = *desc;
-    e->device = devices[0];
-    B2M_CK(cudaSetDevice(e->device));
-    cudaDeviceProp prop;
-    B2M_CK(cudaGetDeviceProperties(&prop, e->device));
-    if (prop.major != 10) {
-      delete e;
-      throw Error(B2M_ERR_CUDA, "libb200mlip is built for sm_100a (B200) only");
+    for (int p = 0; p < ndev; p++) made.push_back(create_one(desc, devices[p], count));
+    b2m_engine* e = made[0];
+    if (ndev > 1) {
+      // single-process group: partition p lives on devices[p] (ordinals may repeat: several partitions on one GPU);
+      // peer access between distinct devices so that halo rows are plain stores into the neighbour's memory
+      for (int p = 0; p < ndev; p++) {
+        made[p]->rank = p, made[p]->world = ndev, made[p]->leader = e;
+        B2M_CK(cudaSetDevice(made[p]->device));
+        made[p]->hev.resize(4 * 16 + 8);  // 2 forward + 2 backward exchange points per block, n_blocks <= 16
+        for (auto& ev : made[p]->hev) B2M_CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (int q = 0; q < ndev; q++) {
+          if (made[q]->device == made[p]->device) continue;
+          int can = 0;
+          B2M_CK(cudaDeviceCanAccessPeer(&can, made[p]->device, made[q]->device));
+          B2M_REQUIRE(can, B2M_ERR_CUDA, "devices of a single-process group need peer access (NVLink / NVSwitch)");
+          cudaError_t pe = cudaDeviceEnablePeerAccess(made[q]->device, 0);
+          if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+          else B2M_CK(pe);
+        }
+      }
+      e->parts = made;
+      B2M_CK(cudaSetDevice(e->device));
     }
-    e->num_sms = prop.multiProcessorCount;
-    {
-      const char* leg = getenv("B2M_LEGACY_FFMA");
-      e->use_tc = !(leg && leg[0] == '1');
-      const char* gen = getenv("B2M_ATOMCONV");
-      e->ac_gen = gen ? atoi(gen) : 3;
-    }
-    B2M_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
-    for (auto& ev : e->ev) B2M_CK(cudaEventCreate(&ev));
     *out = e;
   } catch (const b2m::Error& ex) {
+    for (auto* m : made) delete m;
     g_create_err = ex.what();
     return ex.code;
   }
   return B2M_OK;
 }
 
-int b2m_destroy(b2m_handle h) {
-  if (!h) return B2M_ERR_INVALID;
+static void destroy_one(b2m_engine* h) {
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto& p : h->gather_ev) {
@@ -897,8 +1111,16 @@ int b2m_destroy(b2m_handle h) {
   }
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : h->hev) cudaEventDestroy(ev);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
+}
+
+int b2m_destroy(b2m_handle h) {
+  if (!h) return B2M_ERR_INVALID;
+  std::vector<b2m_engine*> members(h->parts.begin(), h->parts.end());
+  for (size_t p = 1; p < members.size(); p++) destroy_one(members[p]);
+  destroy_one(h);
   return B2M_OK;
 }
 
@@ -910,35 +1132,41 @@ int b2m_load_weights(b2m_handle h, const char* name, const float* host_ptr, cons
   size_t n = 1;
   std::vector<int64_t> sh(shape, shape + ndim);
   for (auto s : sh) n *= (size_t)s;
-  h->host_w[name] = std::vector<float>(host_ptr, host_ptr + n);
-  h->host_shape[name] = sh;
-  h->finalized = false;
+  each_member(h, [&](b2m_engine* e) {
+    e->host_w[name] = std::vector<float>(host_ptr, host_ptr + n);
+    e->host_shape[name] = sh;
+    e->finalized = false;
+  });
   API_END
 }
 
 int b2m_set_element_refs(b2m_handle h, const double* offsets, int n) {
   API_BEGIN
-  if (offsets == nullptr || n == 0) {  // clear: a later Potential without element_refs must not inherit the old offsets
-    h->elem_refs.clear();
-    h->d_eref = nullptr;
-  } else {
-    B2M_REQUIRE(n == h->desc.n_elem, B2M_ERR_INVALID, "element_refs length must equal n_elem");
-    h->elem_refs.assign(offsets, offsets + n);
-  }
-  h->finalized = false;
+  B2M_REQUIRE(offsets == nullptr || n == 0 || n == h->desc.n_elem, B2M_ERR_INVALID, "element_refs length must equal n_elem");
+  each_member(h, [&](b2m_engine* e) {
+    if (offsets == nullptr || n == 0) {  // clear: a later Potential without element_refs must not inherit the old offsets
+      e->elem_refs.clear();
+      e->d_eref = nullptr;
+    } else {
+      e->elem_refs.assign(offsets, offsets + n);
+    }
+    e->finalized = false;
+  });
   API_END
 }
 
 int b2m_set_scaling(b2m_handle h, double data_mean, double data_std) {
   API_BEGIN
-  h->desc.data_mean = data_mean;
-  h->desc.data_std = data_std;
+  each_member(h, [&](b2m_engine* e) {
+    e->desc.data_mean = data_mean;
+    e->desc.data_std = data_std;
+  });
   API_END
 }
 
 int b2m_finalize_weights(b2m_handle h) {
   API_BEGIN
-  finalize_weights(h);
+  each_member(h, [&](b2m_engine* e) { finalize_weights(e); });
   API_END
 }
 
@@ -960,6 +1188,7 @@ int b2m_comm_unique_id(char* out128) {
 int b2m_comm_init(b2m_handle h, const char* id128, int rank, int world) {
   API_BEGIN
   B2M_REQUIRE(world >= 1 && world <= MAXP && rank >= 0 && rank < world, B2M_ERR_PARTITIONS, "bad rank/world");
+  B2M_REQUIRE(h->parts.empty(), B2M_ERR_STATE, "a single-process group (ndev > 1) needs no communicator");
   h->rank = rank;
   h->world = world;
   if (world > 1) {
@@ -976,16 +1205,15 @@ int b2m_set_partition(b2m_handle h, int rank, int world) {
   API_BEGIN
   B2M_REQUIRE(world >= 1 && world <= MAXP && rank >= 0 && rank < world, B2M_ERR_PARTITIONS, "bad rank/world");
   B2M_REQUIRE(h->comm == nullptr, B2M_ERR_STATE, "communicator already initialised");
+  B2M_REQUIRE(h->parts.empty(), B2M_ERR_STATE, "the partitions of a single-process group are fixed by b2m_create");
   h->rank = rank;
   h->world = world;
   h->have_graph = false;
   API_END
 }
 
-int b2m_set_structure(b2m_handle h, int64_t natoms, const double* cart, const double* lattice9,
-                      const int32_t* species, const int* pbc3, double tol) {
-  API_BEGIN
-  B2M_REQUIRE(cart && lattice9 && species && pbc3, B2M_ERR_INVALID, "null structure argument");
+static void set_structure_one(b2m_engine* h, int64_t natoms, const double* cart, const double* lattice9,
+                              const int32_t* species, const int* pbc3, double tol) {
   h->have_graph = false;
   B2M_CK(cudaEventRecord(h->ev[3], h->st));
   h->g.build(h->st, natoms, cart, lattice9, species, pbc3, h->desc.cutoff, h->desc.three_body_cutoff, tol, h->rank,
@@ -997,12 +1225,24 @@ int b2m_set_structure(b2m_handle h, int64_t natoms, const double* cart, const do
   B2M_CK(cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]));
   h->t_graph = ms;
   h->have_graph = true;
+}
+
+int b2m_set_structure(b2m_handle h, int64_t natoms, const double* cart, const double* lattice9,
+                      const int32_t* species, const int* pbc3, double tol) {
+  API_BEGIN
+  B2M_REQUIRE(cart && lattice9 && species && pbc3, B2M_ERR_INVALID, "null structure argument");
+  if (h->parts.empty()) {
+    set_structure_one(h, natoms, cart, lattice9, species, pbc3, tol);
+  } else {  // every partition builds its own slab on its own device, concurrently
+    for_each_part(h, [&](b2m_engine* pe) { set_structure_one(pe, natoms, cart, lattice9, species, pbc3, tol); });
+    for (auto* pe : h->parts) h->t_graph = std::max(h->t_graph, pe->t_graph);
+  }
   API_END
 }
 
 int b2m_compute(b2m_handle h, int want_forces, int want_stress, double* energy, float* forces, float* stress9) {
   API_BEGIN
-  run(h, want_forces || want_stress);
+  run_any(h, want_forces || want_stress);
   fetch(h, energy, want_forces ? forces : nullptr, want_stress ? stress9 : nullptr);
   API_END
 }
@@ -1010,7 +1250,7 @@ int b2m_compute(b2m_handle h, int want_forces, int want_stress, double* energy, 
 int b2m_compute_resident(b2m_handle h, int want_forces, int want_stress, int reps, double* energy, float* ms) {
   API_BEGIN
   B2M_REQUIRE(reps >= 1, B2M_ERR_INVALID, "reps >= 1");
-  for (int r = 0; r < reps; r++) run(h, want_forces || want_stress);
+  for (int r = 0; r < reps; r++) run_any(h, want_forces || want_stress);
   fetch(h, energy, nullptr, nullptr);
   if (ms) *ms = (float)h->t_total;
   API_END
@@ -1019,15 +1259,19 @@ int b2m_compute_resident(b2m_handle h, int want_forces, int want_stress, int rep
 int b2m_get_sitewise(b2m_handle h, float* out) {
   API_BEGIN
   B2M_REQUIRE(h->have_graph && out, B2M_ERR_STATE, "no structure");
+  std::vector<float> full(h->g.N, 0.f);
+  auto collect = [&](b2m_engine* e) {  // owned rows of one partition -> global order
+    Graph& g = e->g;
+    std::vector<float> loc(g.n_own);
+    std::vector<int> gid(g.n_own);
+    B2M_CK(cudaMemcpyAsync(loc.data(), e->site.p, g.n_own * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+    B2M_CK(cudaMemcpyAsync(gid.data(), g.gid.p, g.n_own * sizeof(int), cudaMemcpyDeviceToHost, e->st));
+    B2M_CK(cudaStreamSynchronize(e->st));
+    for (int i = 0; i < g.n_own; i++) full[gid[i]] = loc[i];
+  };
+  each_member(h, collect);
   Graph& g = h->g;
-  std::vector<float> loc(g.n_own);
-  std::vector<int> gid(g.n_own);
-  B2M_CK(cudaMemcpyAsync(loc.data(), h->site.p, g.n_own * sizeof(float), cudaMemcpyDeviceToHost, h->st));
-  B2M_CK(cudaMemcpyAsync(gid.data(), g.gid.p, g.n_own * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-  B2M_CK(cudaStreamSynchronize(h->st));
-  std::vector<float> full(g.N, 0.f);
-  for (int i = 0; i < g.n_own; i++) full[gid[i]] = loc[i];
-  if (h->world > 1) {
+  if (h->world > 1 && h->parts.empty()) {
     B2M_CK(cudaMemcpyAsync(h->site_full.p, full.data(), g.N * sizeof(float), cudaMemcpyHostToDevice, h->st));
     NCCL_CK(g_nccl.AllReduce(h->site_full.p, h->site_full.p, (size_t)g.N, ncclFloat32, ncclSum, h->comm, h->st));
     B2M_CK(cudaMemcpyAsync(full.data(), h->site_full.p, g.N * sizeof(float), cudaMemcpyDeviceToHost, h->st));

@@ -5,7 +5,7 @@
 
 namespace b2m {
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 // ============================================================================================
 // device helpers
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(NT, 2) k_atomconv_fwd(const AtomConvArgs a) {
 void launch_atomconv_fwd(cudaStream_t st, const AtomConvArgs& a) {
   if (a.E <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtomSmemFwd::bytes));
   }
   k_atomconv_fwd<<<cdiv(a.E, TM), NT, AtomSmemFwd::bytes, st>>>(a);
@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(NT, 1) k_atomconv_bwd(const AtomConvArgs a) {
 void launch_atomconv_bwd(cudaStream_t st, const AtomConvArgs& a) {
   if (a.E <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AtomSmemBwd::bytes));
   }
   k_atomconv_bwd<<<cdiv(a.E, TM), NT, AtomSmemBwd::bytes, st>>>(a);
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(NT, 1) k_line_bwd(const LineArgs a) {
 void launch_line_fwd(cudaStream_t st, const LineArgs& a, bool hidden) {
   if (a.A <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_line_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineSmem::fwd_bytes));
     B2M_CK(cudaFuncSetAttribute(k_line_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineSmem::fwd_bytes));
   }
@@ -1027,7 +1027,7 @@ void launch_line_fwd(cudaStream_t st, const LineArgs& a, bool hidden) {
 void launch_line_bwd(cudaStream_t st, const LineArgs& a, bool hidden) {
   if (a.A <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_line_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineSmem::bwd_bytes));
     B2M_CK(cudaFuncSetAttribute(k_line_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineSmem::bwd_bytes));
   }

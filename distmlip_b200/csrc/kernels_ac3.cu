@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_bwd_v3(const AtomConvArgs a
 void launch_atomconv_bwd_v3(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first())
+  if (auto once_ = attr.first(); once_)
     B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ac3BwdSmem::bytes));
   const int64_t ntiles = (a.E + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2, (int64_t)num_sms);
@@ -867,7 +867,7 @@ void launch_atomconv_bwd_v3(cudaStream_t st, const AtomConvArgs& a, const AtomCo
 void launch_atomconv_fwd_v3(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Ac3Smem::bytes));
   }
   const int64_t ntiles = (a.E + 127) / 128;

@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_atomconv_bwd_tc(const AtomConvArgs 
 void launch_atomconv_bwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_atomconv_bwd_tc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdTcSmem::bytes));
   }
@@ -697,7 +697,7 @@ constexpr bool kFwdPrefetchDefault = true;  // measured: 1.087 vs 1.122 ms per l
 void launch_atomconv_fwd_tc(cudaStream_t st, const AtomConvArgs& a, const AtomConvTcW& w, int num_sms) {
   if (a.E <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_atomconv_fwd_tc<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdTcSmem::bytes));
@@ -1281,7 +1281,7 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
 void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms) {
   if (a.A <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_line_fwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_line_fwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
   }
@@ -1299,7 +1299,7 @@ void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bo
 void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms) {
   if (a.A <= 0) return;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_line_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
     B2M_CK(cudaFuncSetAttribute(k_line_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LineTcSmem::bytes));
   }
@@ -1622,7 +1622,7 @@ static void launch_gemm_tc_t(cudaStream_t st, const float* A, int lda, const flo
                              const float* bias, const float* R, int ldr, bool accum, int num_sms) {
   constexpr size_t bytes = (size_t)(64 + 2 * N * K + 128 * 68) * 4;
   static PerDeviceOnce attr;
-  if (attr.first()) {
+  if (auto once_ = attr.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_gemm_tc<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   }
   static const bool pipe = [] {
@@ -1630,7 +1630,7 @@ static void launch_gemm_tc_t(cudaStream_t st, const float* A, int lda, const flo
     return v ? atoi(v) != 0 : true;
   }();
   static PerDeviceOnce attr_pipe;
-  if (pipe && attr_pipe.first()) {
+  if (auto once_ = attr_pipe.first(); once_) {
     B2M_CK(cudaFuncSetAttribute(k_gemm_tc_pipe<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   }
   const int ntiles = (M + 127) / 128;

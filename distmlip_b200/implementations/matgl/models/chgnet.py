@@ -10,9 +10,12 @@ forward/backward run in libb200mlip.so (hand-written sm_100a kernels) instead of
     from one Python thread               (chgnet.py:455-549)     per GPU; weights replicated, never sharded)
   potential_forward_dist + dist_forward  (chgnet.py:21-453)    b2m_compute on the resident graph
 
-One process per GPU: under `torchrun` (torch.distributed initialised, world == len(gpus)) rank r
-drives gpus[r]; a single process may only pass one GPU.  "cpu" entries are rejected: there is no
-CPU path in this engine.
+Two ways to use several GPUs, both behind the reference's call `enable_distributed_mode([0, 1, ...])`:
+  * from ONE process (the reference's own usage, examples/chgnet_example.ipynb cell 1): a single-process group --
+    one partition, host thread and stream per entry of `gpus`, halo rows exchanged as peer-memory stores;
+  * under `torchrun` (torch.distributed initialised, world == len(gpus)): one process per GPU, rank r drives
+    gpus[r], NCCL point-to-point halo exchange.
+"cpu" entries are rejected: there is no CPU path in this engine.
 """
 from __future__ import annotations
 
@@ -71,13 +74,16 @@ class CHGNet_Dist:
         rank, world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        group = False
         if world != len(gpus):
-            if len(gpus) == 1 and world >= 1:
+            if len(gpus) == 1:
                 rank, world = 0, 1  # replica mode: every process runs its own single-GPU engine
+            elif world == 1:
+                group = True        # the reference's usage: one process drives every GPU of the list
             else:
                 raise RuntimeError(
-                    f"enable_distributed_mode({gpus}) needs one process per GPU: launch with "
-                    f"`torchrun --nproc-per-node {len(gpus)}` (torch.distributed world is {world})")
+                    f"enable_distributed_mode({gpus}) inside a {world}-process job: pass one GPU per process "
+                    f"(len(gpus) == world) or a single GPU")
         self.gpus = ["cuda:" + str(g) for g in gpus]
         sd = self._state_dict
         dim = int(sd["atom_embedding.weight"].shape[1])
@@ -100,9 +106,12 @@ class CHGNet_Dist:
             n_elem=int(sd["atom_embedding.weight"].shape[0]), dim=dim, max_n=max_n, max_f=max_f,
             n_blocks=int(self._attr("n_blocks")), cutoff=float(self._attr("cutoff")),
             three_body_cutoff=float(self._attr("three_body_cutoff")),
-            cutoff_exponent=int(self._attr("cutoff_exponent")), device=int(gpus[rank]))
+            cutoff_exponent=int(self._attr("cutoff_exponent")),
+            device=[int(g) for g in gpus] if group else int(gpus[rank]))
         eng.load_state_dict(sd)
-        if world > 1:
+        if group:
+            rank, world = 0, 1  # one host process: results need no cross-process reduction
+        elif world > 1:
             ids = [_lib.comm_unique_id() if rank == 0 else None]
             torch.distributed.broadcast_object_list(ids, src=0)
             eng.comm_init(ids[0], rank, world)

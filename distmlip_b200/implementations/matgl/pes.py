@@ -65,7 +65,7 @@ class Potential_Dist:
         model._finalize(self.data_mean, self.data_std, self.element_refs)
         dist_info = Distributed.create_distributed(
             cart_coords=cart_coords, frac_coords=None, lattice_matrix=lattice_matrix,
-            num_partitions=model._world, pbc=pbc, use_bond_graph=True, cutoff=float(model.cutoff),
+            num_partitions=model._engine.world, pbc=pbc, use_bond_graph=True, cutoff=float(model.cutoff),
             three_body_cutoff=float(model.three_body_cutoff), tol=tol, num_threads=1, engine=model._engine,
             species=species)
         self.last_dist_info = dist_info

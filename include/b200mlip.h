@@ -63,7 +63,15 @@ typedef struct {
   double data_std;
 } b2m_model_desc;
 
-/* devices: CUDA ordinals owned by this handle; ndev must be 1 (one process per GPU). */
+/* devices: CUDA ordinals owned by this handle, one per partition (the reference's
+ * enable_distributed_mode(gpus), chgnet.py:455-549).
+ *   ndev == 1: one partition, or one rank of a multi-process job (b2m_comm_init).
+ *   ndev  > 1: a single-process group: partition p runs on devices[p] (ordinals may repeat, e.g.
+ *              {0, 0} = two partitions on one GPU), one host thread + stream per partition inside
+ *              b2m_set_structure / b2m_compute, halo rows exchanged as direct peer-memory stores
+ *              ordered by CUDA events (no NCCL).  b2m_get_counts / b2m_get_partition_info /
+ *              b2m_debug_tensor then describe partition 0; energies, forces, stress and the
+ *              site-wise readout are those of the whole structure. */
 int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_handle* out);
 int b2m_destroy(b2m_handle h);
 const char* b2m_last_error(b2m_handle h);

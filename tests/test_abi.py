@@ -51,7 +51,8 @@ def test_create_rejects_bad_args(lib):
     assert lib.b2m_create(C.byref(bad), dev, 1, C.byref(h)) == -1
     assert b"dim=64" in lib.b2m_last_error(None)
     ok = _lib.ModelDesc(89, 64, 9, 4, 4, 5, 5.0, 3.0, 0.0, 1.0)
-    assert lib.b2m_create(C.byref(ok), dev, 2, C.byref(h)) == -1  # one process per GPU
+    assert lib.b2m_create(C.byref(ok), dev, 0, C.byref(h)) == -2  # ndev in [1,16] (one ordinal per partition)
+    assert lib.b2m_create(C.byref(ok), dev, 17, C.byref(h)) == -2
     assert lib.b2m_create(None, dev, 1, C.byref(h)) == -1
     bondgt = _lib.ModelDesc(89, 64, 9, 4, 4, 5, 3.0, 5.0, 0.0, 1.0)  # bond_r > r (fpis.c:436)
     assert lib.b2m_create(C.byref(bondgt), dev, 1, C.byref(h)) == -1

@@ -96,11 +96,16 @@ def test_halo_protocol_world2_gloo():
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
-def test_enable_distributed_mode_requires_one_process_per_gpu():
+def test_enable_distributed_mode_from_one_process_asks_for_a_group():
+    """the reference's own call (examples/chgnet_example.ipynb cell 1): one process, several GPUs -> a single-process
+    group (b2m_create with ndev = len(gpus)); without a GPU that fails loudly in b2m_create, never on the host side"""
+    from distmlip_b200 import _lib
     from distmlip_b200.implementations.matgl import CHGNet_Dist
     from tests._util import make_model
 
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_group.py")
     m = CHGNet_Dist.from_existing(make_model())
-    with pytest.raises(RuntimeError) as ei:
-        m.enable_distributed_mode([0, 1])  # single process, two GPUs
-    assert "one process per GPU" in str(ei.value)
+    with pytest.raises(_lib.B2MError) as ei:
+        m.enable_distributed_mode([0, 1])
+    assert "no CUDA device" in str(ei.value)
