@@ -218,7 +218,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def parity_block(atoms, out, pot_factory, rank, world, local):
+def parity_block(atoms, out, pot_factory, rank, world, local, release=None):
     """Correctness evidence computed in the run (outside the timed region).  Always: net force, virial symmetry,
     energy per atom, checksum of the forces of 4096 seeded atoms.  At N > 1 rank 0 also evaluates the same cell on a
     single partition (its own GPU, a second engine) and reports the difference of E and of every force component."""
@@ -238,6 +238,8 @@ def parity_block(atoms, out, pot_factory, rank, world, local):
     }
     if world > 1 and rank == 0:
         try:
+            if release is not None:
+                release()  # this rank's own partition is not needed any more: give its memory to the check
             free, _tot = torch.cuda.mem_get_info()
             pot1 = pot_factory()
             o1 = pot1(atoms)
@@ -337,12 +339,12 @@ def run_ours(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = t2.item()
     e2e_val = natoms / (e2e_ms * 1e-3)
-    tm = eng.timings()
-    parity = parity_block(atoms, out, single_partition_potential, rank, world, local)
+    c_final, tm = eng.counts(), eng.timings()
+    parity = parity_block(atoms, out, single_partition_potential, rank, world, local, release=eng.release_workspace)
     barrier()
 
     if rank == 0:
-        c = eng.counts()
+        c = c_final
         peak, peak_src = load_peaks()
         g_ms = float(np.mean(gather_ms))
         alg_bytes = SURVEY_BYTES_PER_EDGE * c["n_edges"]

@@ -17,7 +17,7 @@ SYMBOLS = [
     "b2m_create", "b2m_destroy", "b2m_last_error", "b2m_load_weights", "b2m_set_element_refs",
     "b2m_finalize_weights", "b2m_set_scaling", "b2m_comm_unique_id", "b2m_comm_init", "b2m_set_partition", "b2m_set_structure", "b2m_compute",
     "b2m_compute_resident", "b2m_get_sitewise", "b2m_get_counts", "b2m_get_partition_info",
-    "b2m_debug_tensor", "b2m_last_timings",
+    "b2m_debug_tensor", "b2m_last_timings", "b2m_release_workspace",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library():
     lib.b2m_get_partition_info.restype = i64
     lib.b2m_debug_tensor.argtypes = [vp, C.c_char_p, P(C.c_float), i64, P(i64), P(i64)]
     lib.b2m_last_timings.argtypes = [vp, P(dbl), i32]
+    lib.b2m_release_workspace.argtypes = [vp]
     for s in SYMBOLS:
         if s not in ("b2m_last_error", "b2m_get_partition_info"):
             getattr(lib, s).restype = C.c_int
@@ -230,6 +231,10 @@ class Engine:
         self._ck(self.lib.b2m_debug_tensor(self.h, name.encode(), out.ctypes.data_as(C.POINTER(C.c_float)), cap,
                                            C.byref(r), C.byref(k)))
         return out[: r.value * k.value].reshape(r.value, k.value).copy()
+
+    def release_workspace(self):
+        """free the resident graph and all per-structure device buffers (the next set_structure allocates again)"""
+        self._ck(self.lib.b2m_release_workspace(self.h))
 
     def timings(self):
         out = (C.c_double * 5)()

@@ -14,6 +14,7 @@
 #include <thread>
 #include <cstring>
 #include <map>
+#include <new>
 #include <set>
 #include <string>
 #include <vector>
@@ -113,6 +114,8 @@ struct b2m_engine {
   b2m_model_desc desc;
   int device = 0;
   cudaStream_t st = nullptr;
+  cudaStream_t cst = nullptr;            // halo traffic of the forward pass (overlaps the projections that do not need it)
+  cudaEvent_t ev_prod = nullptr, ev_halo = nullptr;
   std::string err;
   // weights
   std::map<std::string, std::vector<float>> host_w;
@@ -552,8 +555,12 @@ static cudaEvent_t next_halo_event(b2m_engine* e) {
   return e->hev[e->hpoint];
 }
 
-// forward: rows of tensor (bonds ? h : x)[l] listed in to_list[q] -> q's halo section; my halo section <- owners
-static void halo_forward(b2m_engine* e, bool bonds, int l) {
+// forward: rows of tensor (bonds ? h : x)[l] listed in to_list[q] -> q's halo section; my halo section <- owners.
+// Split in two so that the exchange runs on the engine's second stream while the compute stream does the projections
+// that do not read the halo rows (the reference issues its copies on the compute stream, dist.py:344-356):
+//   halo_forward_begin: [compute: producer done] -> [comm stream: pack, send / receive or peer stores]
+//   halo_forward_end  : compute stream waits for the exchange (and, in a group, for the neighbours' stores)
+static void halo_forward_begin(b2m_engine* e, bool bonds, int l) {
   if (e->world <= 1) return;
   Graph& g = e->g;
   float* buf = halo_buffer(e, bonds, l);
@@ -563,6 +570,8 @@ static void halo_forward(b2m_engine* e, bool bonds, int l) {
   const int* foff = bonds ? g.bfrom_off : g.from_off;
   const int* list = bonds ? g.bto_list.p : g.to_list.p;
   const size_t base = bonds ? (size_t)g.B_own : (size_t)g.n_own;
+  B2M_CK(cudaEventRecord(e->ev_prod, e->st));
+  B2M_CK(cudaStreamWaitEvent(e->cst, e->ev_prod, 0));
   if (e->leader != nullptr) {
     b2m_engine* L = e->leader;
     for (int q = 0; q < e->world; q++) {
@@ -573,27 +582,35 @@ static void halo_forward(b2m_engine* e, bool bonds, int l) {
       B2M_REQUIRE(pn == nto[q], B2M_ERR_STATE, "halo sections of two partitions disagree");
       const size_t pbase = bonds ? (size_t)pg.B_own : (size_t)pg.n_own;
       const size_t pfoff = bonds ? (size_t)pg.bfrom_off[e->rank] : (size_t)pg.from_off[e->rank];
-      launch_gather_rows(e->st, nto[q], D, list + toff[q], buf, halo_buffer(pe, bonds, l) + (pbase + pfoff) * D);
+      launch_gather_rows(e->cst, nto[q], D, list + toff[q], buf, halo_buffer(pe, bonds, l) + (pbase + pfoff) * D);
     }
-    cudaEvent_t ev = next_halo_event(e);
-    B2M_CK(cudaEventRecord(ev, e->st));
-    const int k = e->hpoint++;
-    L->gsync.arrive_and_wait();  // every partition has recorded its event for this point
-    for (int q = 0; q < e->world; q++)  // (every partition records an event at every point: waiting on all is always valid)
-      if (q != e->rank) B2M_CK(cudaStreamWaitEvent(e->st, L->parts[q]->hev[k], 0));
+    B2M_CK(cudaEventRecord(next_halo_event(e), e->cst));
     return;
   }
   for (int q = 0; q < e->world; q++)
-    if (nto[q] > 0) launch_gather_rows(e->st, nto[q], D, list + toff[q], buf, e->sendbuf.p + (size_t)toff[q] * D);
+    if (nto[q] > 0) launch_gather_rows(e->cst, nto[q], D, list + toff[q], buf, e->sendbuf.p + (size_t)toff[q] * D);
   NCCL_CK(g_nccl.GroupStart());
   for (int q = 0; q < e->world; q++) {
     if (q == e->rank) continue;
     if (nto[q] > 0)
-      NCCL_CK(g_nccl.Send(e->sendbuf.p + (size_t)toff[q] * D, (size_t)nto[q] * D, ncclFloat32, q, e->comm, e->st));
+      NCCL_CK(g_nccl.Send(e->sendbuf.p + (size_t)toff[q] * D, (size_t)nto[q] * D, ncclFloat32, q, e->comm, e->cst));
     if (nfrom[q] > 0)
-      NCCL_CK(g_nccl.Recv(buf + (base + foff[q]) * D, (size_t)nfrom[q] * D, ncclFloat32, q, e->comm, e->st));
+      NCCL_CK(g_nccl.Recv(buf + (base + foff[q]) * D, (size_t)nfrom[q] * D, ncclFloat32, q, e->comm, e->cst));
   }
   NCCL_CK(g_nccl.GroupEnd());
+  B2M_CK(cudaEventRecord(e->ev_halo, e->cst));
+}
+static void halo_forward_end(b2m_engine* e) {
+  if (e->world <= 1) return;
+  if (e->leader != nullptr) {
+    b2m_engine* L = e->leader;
+    const int k = e->hpoint++;
+    L->gsync.arrive_and_wait();  // every partition has recorded its event for this point
+    for (int q = 0; q < e->world; q++)  // own event too: my stores must precede any later reuse of the source rows
+      B2M_CK(cudaStreamWaitEvent(e->st, L->parts[q]->hev[k], 0));
+    return;
+  }
+  B2M_CK(cudaStreamWaitEvent(e->st, e->ev_halo, 0));
 }
 // backward: my halo rows of the adjoint -> owners (accumulate), then zero the halo rows
 static void halo_backward(b2m_engine* e, float* gbuf, bool bonds) {
@@ -760,15 +777,23 @@ static void line_fwd_dispatch(b2m_engine* e, int l, bool hidden, const LineArgs&
   else
     launch_line_fwd(e->st, a, hidden);
 }
-static void line_projections(b2m_engine* e, int l, bool hidden) {
-  Graph& g = e->g;
+// first-layer projections of the line-graph MLPs: Ha / Hb from the bond features, Xc from the atom features
+static void line_proj_Ha(b2m_engine* e, int l, bool hidden) {
   const BondLayerW& w = e->bw[l];
   const float* hsrc = hidden ? e->h[l].p : e->h[l + 1].p;
-  gemm(e, hsrc, D, hidden ? w.W1a_k : w.WAa_k, e->Ha.p, D2, g.B_loc, D2, D, nullptr, nullptr, 0, false);
-  gemm(e, hsrc, D, hidden ? w.W1b_k : w.WAb_k, e->Hb.p, D2, g.B_own, D2, D, hidden ? w.b1 : w.bA, nullptr,
-              0, false);
-  gemm(e, e->x[l + 1].p, D, hidden ? w.W1c_k : w.WAc_k, e->Xc.p, D2, g.n_loc, D2, D, nullptr, nullptr, 0,
-              false);
+  gemm(e, hsrc, D, hidden ? w.W1a_k : w.WAa_k, e->Ha.p, D2, e->g.B_loc, D2, D, nullptr, nullptr, 0, false);
+}
+static void line_proj_Hb(b2m_engine* e, int l, bool hidden) {
+  const BondLayerW& w = e->bw[l];
+  const float* hsrc = hidden ? e->h[l].p : e->h[l + 1].p;
+  gemm(e, hsrc, D, hidden ? w.W1b_k : w.WAb_k, e->Hb.p, D2, e->g.B_own, D2, D, hidden ? w.b1 : w.bA, nullptr, 0, false);
+}
+static void line_proj_Xc(b2m_engine* e, int l, bool hidden) {
+  const BondLayerW& w = e->bw[l];
+  gemm(e, e->x[l + 1].p, D, hidden ? w.W1c_k : w.WAc_k, e->Xc.p, D2, e->g.n_loc, D2, D, nullptr, nullptr, 0, false);
+}
+static void line_projections(b2m_engine* e, int l, bool hidden) {
+  line_proj_Ha(e, l, hidden), line_proj_Hb(e, l, hidden), line_proj_Xc(e, l, hidden);
 }
 static void line_bwd_common(b2m_engine* e, int l, bool hidden, LineArgs& a) {
   Graph& g = e->g;
@@ -795,9 +820,12 @@ static void forward(b2m_engine* e) {
   launch_angle_init(e->st, g.A, g.a_in.p, g.a_out.p, g.b_vec.p, e->d_fa, e->d_Wae, e->ang[0].p);
   for (int l = 0; l < nb - 1; l++) {
     atom_layer_fwd(e, l);
-    halo_forward(e, false, l + 1);
     const BondLayerW& w = e->bw[l];
-    line_projections(e, l, true);
+    // x^{l+1} halo rows travel while the two projections of the bond features run (they do not read x)
+    halo_forward_begin(e, false, l + 1);
+    line_proj_Ha(e, l, true), line_proj_Hb(e, l, true);
+    halo_forward_end(e);
+    line_proj_Xc(e, l, true);
     launch_zero_rows(e->st, e->aggB.p, (int64_t)g.B_own * D);
     LineArgs a = line_args(e, l, true);
     a.aggB = e->aggB.p;
@@ -807,8 +835,11 @@ static void forward(b2m_engine* e) {
     if (l < nb - 2) {
       // the last block's angle update (and the halo copy of h feeding it) is dead code in the
       // reference (chgnet.py:353-368 on the last iteration): nothing reads it afterwards.
-      halo_forward(e, true, l + 1);
-      line_projections(e, l, false);
+      // h^{l+1} halo rows travel while Hb (owned bonds only) and Xc (atoms) are projected; Ha reads the halo rows
+      halo_forward_begin(e, true, l + 1);
+      line_proj_Hb(e, l, false), line_proj_Xc(e, l, false);
+      halo_forward_end(e);
+      line_proj_Ha(e, l, false);
       LineArgs b = line_args(e, l, false);
       b.ang_out = e->ang[l + 1].p;
       line_fwd_dispatch(e, l, false, b);
@@ -1047,6 +1078,9 @@ static b2m_engine* create_one(const b2m_model_desc* desc, int device, int count)
     const char* gen = getenv("B2M_ATOMCONV");
     e->ac_gen = gen ? atoi(gen) : 3;
     B2M_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    B2M_CK(cudaStreamCreateWithFlags(&e->cst, cudaStreamNonBlocking));
+    B2M_CK(cudaEventCreateWithFlags(&e->ev_prod, cudaEventDisableTiming));
+    B2M_CK(cudaEventCreateWithFlags(&e->ev_halo, cudaEventDisableTiming));
     for (auto& ev : e->ev) B2M_CK(cudaEventCreate(&ev));
   } catch (...) {
     delete e;
@@ -1112,6 +1146,9 @@ static void destroy_one(b2m_engine* h) {
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->hev) cudaEventDestroy(ev);
+  if (h->ev_prod) cudaEventDestroy(h->ev_prod);
+  if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  if (h->cst) cudaStreamDestroy(h->cst);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
 }
@@ -1345,6 +1382,28 @@ int b2m_debug_tensor(b2m_handle h, const char* name, float* out, int64_t cap, in
   B2M_CK(cudaMemcpyAsync(out, src, r * c * sizeof(float), cudaMemcpyDeviceToHost, h->st));
   B2M_CK(cudaStreamSynchronize(h->st));
   *rows = r, *cols = c;
+  API_END
+}
+
+int b2m_release_workspace(b2m_handle h) {
+  API_BEGIN
+  each_member(h, [&](b2m_engine* e) {
+    B2M_CK(cudaStreamSynchronize(e->st));
+    e->have_graph = false;
+    auto drop = [](auto& b) {
+      if (b.p) cudaFree(b.p);
+      b.p = nullptr, b.cap = 0;
+    };
+    for (auto* v : {&e->x, &e->h, &e->ang, &e->upd, &e->uv, &e->uvB, &e->dsB, &e->uvA, &e->ApL, &e->CpL, &e->QpL})
+      for (auto& b : *v) drop(b);
+    for (auto* b : {&e->be_e, &e->dbe_e, &e->Ha, &e->Hb, &e->Xc, &e->agg, &e->aggB, &e->y1p, &e->y1, &e->y2p, &e->y2,
+                    &e->e_atom, &e->site, &e->gx, &e->gh, &e->gang, &e->gA, &e->gC, &e->gQ, &e->gHa, &e->gHb, &e->gXc,
+                    &e->gagg, &e->gupd, &e->gaggB, &e->gd, &e->gdb, &e->gbvec, &e->gy1, &e->gy2, &e->forces,
+                    &e->sendbuf, &e->recvbuf, &e->site_full, &e->precv[0], &e->precv[1], &e->ftmp})
+      drop(*b);
+    e->g.~Graph();  // the resident graph goes too
+    new (&e->g) Graph();
+  });
   API_END
 }
 

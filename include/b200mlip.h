@@ -127,6 +127,10 @@ int64_t b2m_get_partition_info(b2m_handle h, int which, int64_t* out, int64_t ca
 /* Debug taps (tests only): copies a named device tensor to host (fp32). rows/cols returned. */
 int b2m_debug_tensor(b2m_handle h, const char* name, float* out, int64_t cap, int64_t* rows, int64_t* cols);
 
+/* Frees the resident graph and every per-structure device buffer (weights, streams and communicators stay); the next
+ * b2m_set_structure allocates again.  For callers that want the memory back between structures of very different size. */
+int b2m_release_workspace(b2m_handle h);
+
 /* Per-phase device timings (ms) of the last b2m_compute: [0]=graph build [1]=forward [2]=backward
  * [3]=edge-gather (atom conv fwd) kernel average [4]=total */
 int b2m_last_timings(b2m_handle h, double* out, int n);
