@@ -344,6 +344,26 @@ def test_other_block_counts(nb):
     e.close()
 
 
+def test_release_workspace_then_reuse(model):
+    """b2m_release_workspace frees the resident graph and every per-structure buffer; the handle keeps its weights and the
+    next set_structure allocates again (bench.py uses it to make room for its single-partition check)"""
+    import torch as _t
+
+    e = engine_from_model(model)
+    atoms = si_diamond(6, seed=41)
+    E1, F1, S1 = run_engine(e, model, atoms)
+    used = _t.cuda.mem_get_info()[0]
+    e.release_workspace()
+    assert _t.cuda.mem_get_info()[0] > used  # memory came back
+    from distmlip_b200._lib import B2MError
+
+    with pytest.raises(B2MError):
+        e.compute(True, True)  # no structure any more: an error, not a crash
+    E2, F2, S2 = run_engine(e, model, atoms)
+    assert abs(E1 - E2) / len(atoms) < 2e-8 and np.abs(F1 - F2).max() < 1e-6
+    e.close()
+
+
 def test_empty_and_degenerate_inputs(eng, model):
     from distmlip_b200._lib import B2MError
 
