@@ -498,7 +498,8 @@ static void alloc_workspace(b2m_engine* e) {
   e->upd.resize(nb - 1);
   for (auto& b : e->x) b.ensure(nl * D + 64);
   for (auto& b : e->h) b.ensure(bl * D + 64);
-  for (auto& b : e->ang) b.ensure(A * D + 64);
+  const size_t Apad = (A + 127) / 128 * 128;  // tile-interleaved on the tcgen05 path: whole tiles
+  for (auto& b : e->ang) b.ensure(Apad * D + 64);
   for (auto& b : e->upd) b.ensure(bo * D + 64);
   e->uv.resize(nb);
   if (e->use_tc)
@@ -520,7 +521,7 @@ static void alloc_workspace(b2m_engine* e) {
   e->agg.ensure(no * D + 64), e->aggB.ensure(bo * D + 64);
   e->y1p.ensure(no * D), e->y1.ensure(no * D), e->y2p.ensure(no * D), e->y2.ensure(no * D);
   e->e_atom.ensure(no), e->site.ensure(no);
-  e->gx.ensure(nl * D + 64), e->gh.ensure(bl * D + 64), e->gang.ensure(A * D + 64);
+  e->gx.ensure(nl * D + 64), e->gh.ensure(bl * D + 64), e->gang.ensure(Apad * D + 64);
   e->gA.ensure(nl * D2 + 64), e->gC.ensure(no * D2 + 64), e->gQ.ensure(bo * D2 + 64);
   e->gHa.ensure(bl * D2 + 64), e->gHb.ensure(bo * D2 + 64), e->gXc.ensure(nl * D2 + 64);
   e->gagg.ensure(no * D + 64), e->gupd.ensure(bo * D + 64), e->gaggB.ensure(bo * D + 64);
@@ -817,7 +818,7 @@ static void forward(b2m_engine* e) {
   if (e->use_tc) launch_edge_basis(e->st, g.E, g.e_vec.p, e->rp2, e->be_e.p, e->dbe_e.p);
   launch_embed(e->st, g.n_loc, g.type.p, e->d_emb, e->x[0].p);
   launch_bond_init(e->st, g.B_loc, g.b_vec.p, e->rp2, e->d_Wbe, e->h[0].p);
-  launch_angle_init(e->st, g.A, g.a_in.p, g.a_out.p, g.b_vec.p, e->d_fa, e->d_Wae, e->ang[0].p);
+  launch_angle_init(e->st, g.A, g.a_in.p, g.a_out.p, g.b_vec.p, e->d_fa, e->d_Wae, e->ang[0].p, e->use_tc);
   for (int l = 0; l < nb - 1; l++) {
     atom_layer_fwd(e, l);
     const BondLayerW& w = e->bw[l];
@@ -865,7 +866,7 @@ static void backward(b2m_engine* e) {
   launch_zero_rows(e->st, e->gdb.p, g.B_loc);
   launch_zero_rows(e->st, e->gbvec.p, (int64_t)g.B_loc * 3);
   launch_zero_rows(e->st, e->gh.p, (int64_t)g.B_loc * D);
-  launch_zero_rows(e->st, e->gang.p, g.A * D);
+  launch_zero_rows(e->st, e->gang.p, (g.A + 127) / 128 * 128 * D);
   launch_zero_rows(e->st, e->gx.p, (int64_t)g.n_loc * D);
   launch_zero_rows(e->st, e->forces.p, g.N * 3);
   // readout backward
@@ -895,7 +896,7 @@ static void backward(b2m_engine* e) {
   }
   // geometry: h0 = W_be be(d_b), theta/Fourier, then edges -> forces and virial
   launch_h0_bwd(e->st, g.B_loc, g.b_vec.p, e->rp2, e->d_Wbe, e->gh.p, e->gdb.p);
-  launch_angle_init_bwd(e->st, g.A, g.a_in.p, g.a_out.p, g.b_vec.p, e->d_fa, e->d_Wae, e->gang.p, e->gbvec.p);
+  launch_angle_init_bwd(e->st, g.A, g.a_in.p, g.a_out.p, g.b_vec.p, e->d_fa, e->d_Wae, e->gang.p, e->gbvec.p, e->use_tc);
   launch_edge_final(e->st, g.E, g.e_src.p, g.e_dst.p, g.e_bond.p, g.e_vec.p, g.gid.p, e->gd.p, e->gdb.p, e->gbvec.p,
                     e->forces.p, e->scal.p + 1);
   launch_halo_bond_final(e->st, g.B_own, g.B_loc, g.b_src_gid.p, g.b_dst.p, g.b_vec.p, g.gid.p, e->gdb.p, e->gbvec.p,
@@ -1379,8 +1380,18 @@ int b2m_debug_tensor(b2m_handle h, const char* name, float* out, int64_t cap, in
     throw Error(B2M_ERR_INVALID, "unknown debug tensor: " + n);
   }
   B2M_REQUIRE(r * c <= cap, B2M_ERR_INVALID, "debug buffer too small");
-  B2M_CK(cudaMemcpyAsync(out, src, r * c * sizeof(float), cudaMemcpyDeviceToHost, h->st));
-  B2M_CK(cudaStreamSynchronize(h->st));
+  const bool angle_tensor = n.rfind("ang", 0) == 0 || n == "gang";
+  if (angle_tensor && h->use_tc) {  // tile-interleaved on the device: hand the caller the logical [A][64] rows
+    const size_t padded = (size_t)(r + 127) / 128 * 128 * 64;
+    std::vector<float> tmp(padded);
+    B2M_CK(cudaMemcpyAsync(tmp.data(), src, padded * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    B2M_CK(cudaStreamSynchronize(h->st));
+    for (int64_t i = 0; i < r; i++)
+      for (int k = 0; k < 64; k++) out[i * 64 + k] = tmp[ang_index(i, k, 1)];
+  } else {
+    B2M_CK(cudaMemcpyAsync(out, src, r * c * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    B2M_CK(cudaStreamSynchronize(h->st));
+  }
   *rows = r, *cols = c;
   API_END
 }

@@ -285,7 +285,7 @@ __device__ __forceinline__ AngleGeom angle_geom(const float4 a, const float4 b) 
 __global__ void __launch_bounds__(256) k_angle_init(int64_t na, const int* __restrict__ a_in,
                                                     const int* __restrict__ a_out, const float4* __restrict__ b_vec,
                                                     const float* __restrict__ fa, const float* __restrict__ Wae,
-                                                    float* __restrict__ ang0) {
+                                                    float* __restrict__ ang0, int il) {
   __shared__ float f_s[32][12];
   __shared__ float Ws[64 * 9];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
@@ -314,13 +314,13 @@ __global__ void __launch_bounds__(256) k_angle_init(int64_t na, const int* __res
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < 9; k++) s = fmaf(f_s[r][k], Ws[c * 9 + k], s);
-    ang0[(size_t)(r0 + r) * 64 + c] = s;
+    ang0[ang_index(r0 + r, c, il)] = s;
   }
 }
 void launch_angle_init(cudaStream_t st, int64_t na, const int* a_in, const int* a_out, const float4* b_vec,
-                       const float* fa, const float* Wae, float* ang0) {
+                       const float* fa, const float* Wae, float* ang0, bool interleaved) {
   if (na <= 0) return;
-  k_angle_init<<<cdiv(na, 32), 256, 0, st>>>(na, a_in, a_out, b_vec, fa, Wae, ang0);
+  k_angle_init<<<cdiv(na, 32), 256, 0, st>>>(na, a_in, a_out, b_vec, fa, Wae, ang0, interleaved ? 1 : 0);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(256) k_angle_init_bwd(int64_t na, const int* _
                                                         const int* __restrict__ a_out,
                                                         const float4* __restrict__ b_vec, const float* __restrict__ fa,
                                                         const float* __restrict__ Wae, const float* __restrict__ gang0,
-                                                        float* __restrict__ gbvec) {
+                                                        float* __restrict__ gbvec, int il) {
   __shared__ float gf_s[32][12];
   __shared__ float Ws[64 * 9];
   __shared__ float G[32][65];
@@ -1138,7 +1138,7 @@ __global__ void __launch_bounds__(256) k_angle_init_bwd(int64_t na, const int* _
   for (int i = tid; i < 576; i += 256) Ws[i] = Wae[i];
   for (int i = tid; i < 32 * 64; i += 256) {
     const int r = i >> 6, c = i & 63;
-    G[r][c] = (r0 + r < na) ? gang0[(size_t)(r0 + r) * 64 + c] : 0.f;
+    G[r][c] = (r0 + r < na) ? gang0[ang_index(r0 + r, c, il)] : 0.f;
   }
   __syncthreads();
   for (int i = tid; i < 32 * 9; i += 256) {
@@ -1176,9 +1176,9 @@ __global__ void __launch_bounds__(256) k_angle_init_bwd(int64_t na, const int* _
   }
 }
 void launch_angle_init_bwd(cudaStream_t st, int64_t na, const int* a_in, const int* a_out, const float4* b_vec,
-                           const float* fa, const float* Wae, const float* gang0, float* gbvec) {
+                           const float* fa, const float* Wae, const float* gang0, float* gbvec, bool interleaved) {
   if (na <= 0) return;
-  k_angle_init_bwd<<<cdiv(na, 32), 256, 0, st>>>(na, a_in, a_out, b_vec, fa, Wae, gang0, gbvec);
+  k_angle_init_bwd<<<cdiv(na, 32), 256, 0, st>>>(na, a_in, a_out, b_vec, fa, Wae, gang0, gbvec, interleaved ? 1 : 0);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }

@@ -31,8 +31,17 @@ void launch_gemm(cudaStream_t st, const float* A, int lda, const float* B, float
 void launch_embed(cudaStream_t st, int n, const int* type, const float* emb, float* x0);
 void launch_bond_init(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp, const float* W /*[64][9]*/,
                       float* out /*[nb,64]*/);
+// Angle features (ang^l, and their adjoint gang) are touched only by the line-graph kernels, whose TMEM-imposed
+// thread = row mapping makes every 16-byte access of a row-major [A][64] tensor its own L1 wavefront (LSU 49-63 % busy,
+// profiles/r02k).  On the tcgen05 path they are therefore stored TILE-INTERLEAVED like the other kernel-private tensors:
+//   float4 index ((tile * 16 + c/4) * 128 + r), tile = row / 128, r = row % 128   (a tile is one contiguous 32 KB block)
+// The FP32-FFMA generation keeps row-major; `interleaved` selects the layout in the two kernels both paths share.
+__host__ __device__ inline size_t ang_index(int64_t row, int c, int interleaved) {
+  return interleaved ? ((size_t)((row >> 7) * 16 + (c >> 2)) * 128 + (size_t)(row & 127)) * 4 + (size_t)(c & 3)
+                     : (size_t)row * 64 + (size_t)c;
+}
 void launch_angle_init(cudaStream_t st, int64_t na, const int* a_in, const int* a_out, const float4* b_vec,
-                       const float* fa /*[5]*/, const float* Wae /*[64][9]*/, float* ang0);
+                       const float* fa /*[5]*/, const float* Wae /*[64][9]*/, float* ang0, bool interleaved);
 void launch_silu(cudaStream_t st, int64_t n, const float* pre, float* out);
 void launch_dsilu_mul(cudaStream_t st, int64_t n, const float* pre, float* g);  // g *= dsilu(pre)
 void launch_zero_rows(cudaStream_t st, float* p, int64_t nfloats);
@@ -115,7 +124,7 @@ void launch_h0_bwd(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp
                    float* gdb);
 // theta / Fourier backward: gbvec[a], gbvec[b] += ...
 void launch_angle_init_bwd(cudaStream_t st, int64_t na, const int* a_in, const int* a_out, const float4* b_vec,
-                           const float* fa, const float* Wae, const float* gang0, float* gbvec);
+                           const float* fa, const float* Wae, const float* gang0, float* gbvec, bool interleaved);
 
 // -------- readout --------
 // e_atom = y2 @ F2 + c2 (+elem ref); energy (double) += sum; site = x @ Ws + bs

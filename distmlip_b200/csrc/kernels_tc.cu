@@ -739,8 +739,8 @@ struct LineTcSmem {
   static constexpr int kWA = 64;                    // 16384 floats: fwd: Wg can   | bwd: WgT can (4 x 4096)
   static constexpr int kWB = kWA + 16384;           // 16384 floats: fwd: W2 can   | bwd: W2T can
   static constexpr int kB2 = kWB + 16384;           // 128
-  static constexpr int kGrp = kB2 + 128;            // per group: stage [64][65] + 3 x 128 ints
-  static constexpr int kGrpSize = 64 * 65 + 3 * 128;
+  static constexpr int kGrp = kB2 + 128;            // per group: stage [64][65] + 2 x 3 x 128 ints (double-buffered)
+  static constexpr int kGrpSize = 64 * 65 + 2 * 3 * 128;
   static constexpr int kTotal = kGrp + 2 * kGrpSize;
   static constexpr size_t bytes = (size_t)kTotal * 4;
 };
@@ -771,6 +771,11 @@ __global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const 
     for (int i = 0; i < 6; i++) mbar_init_(&mbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (gt < 128) {  // indices of my first tile (later tiles: prefetched one tile ahead inside the loop)
+    const int64_t e = (2 * (int64_t)blockIdx.x + g) * 128 + gt;
+    const bool ok = e < a.A;
+    s_a[gt] = ok ? a.a_in[e] : 0, s_b[gt] = ok ? a.a_out[e] : -1, s_c[gt] = ok ? a.a_ctr[e] : 0;
+  }
   for (int i = tid; i < 4096; i += 512) reinterpret_cast<float4*>(WAs)[i] = reinterpret_cast<const float4*>(w.Wgcan)[i];
   if (HIDDEN)
     for (int i = tid; i < 4096; i += 512) reinterpret_cast<float4*>(WBs)[i] = reinterpret_cast<const float4*>(w.W2can)[i];
@@ -786,35 +791,25 @@ __global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const 
   uint32_t phase = 0;
 
   const int64_t ntiles = (a.A + 127) / 128;
-  for (int64_t t = 2 * (int64_t)blockIdx.x + g; t < ntiles; t += 2 * (int64_t)gridDim.x) {
+  const int64_t tstride = 2 * (int64_t)gridDim.x;
+  int* idxb = s_a;  // [2][a | b | c][128]
+  int buf = 0;
+  for (int64_t t = 2 * (int64_t)blockIdx.x + g; t < ntiles; t += tstride, buf ^= 1) {
     const int64_t r0 = t * 128;
     const int nvalid = (int)min((int64_t)128, a.A - r0);
-    if (gt < 128) {
-      int ia = 0, ib = -1, ic = 0;
-      if (gt < nvalid) {
-        ia = a.a_in[r0 + gt];
-        ib = a.a_out[r0 + gt];
-        ic = a.a_ctr[r0 + gt];
-      }
-      s_a[gt] = ia;
-      s_b[gt] = ib;
-      s_c[gt] = ic;
+    const int64_t tn = t + tstride;
+    s_a = idxb + buf * 384, s_b = s_a + 128, s_c = s_a + 256;
+    // indices of my next tile: requested now, parked in registers, published at the end of this tile (their DRAM latency
+    // used to sit in front of every tile)
+    int nia = 0, nib = -1, nic = 0;
+    if (tn < ntiles && gt < 128 && tn * 128 + gt < a.A) nia = a.a_in[tn * 128 + gt], nib = a.a_out[tn * 128 + gt], nic = a.a_ctr[tn * 128 + gt];
+    if (tn < ntiles) {
+      // the next tile's angle rows are one contiguous 32 KB block (tile-interleaved layout): DRAM -> L2 now
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.ang + tn * (128 * 64)) + gt * 128));
     }
-    if (w.l2pf) {
-      const int64_t tn = t + 2 * (int64_t)gridDim.x;
-      if (tn * 128 + 128 <= a.A) {
-        l2_prefetch(a.ang + tn * (128 * 64), 128 * 64 * 4, gt, 256);
-        if (gt >= 128 && gt < 140) {
-          const int which = (gt - 128) >> 2, line = (gt - 128) & 3;
-          const int* base = which == 0 ? a.a_in : which == 1 ? a.a_out : a.a_ctr;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + tn * 128 + line * 32));
-        }
-      }
-    }
-    gbar(g);
     const bool valid = r < nvalid;
     const int ia = s_a[r], ib = s_b[r], ic = s_c[r];
-    const float* angrow = a.ang + (size_t)(valid ? r0 + r : 0) * D;
+    const float4* ang4 = reinterpret_cast<const float4*>(a.ang);  // tile-interleaved: (tile, c/4, row) -> coalesced
     float angv[32];
     {  // my half of the angle row -> TMEM operand (hi | lo)
 #pragma unroll
@@ -822,7 +817,7 @@ __global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const 
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          float4 x = *reinterpret_cast<const float4*>(angrow + c0 + ch * 16 + i * 4);
+          float4 x = ang4[tl4<16>(t, r, c0 + ch * 16 + i * 4)];
           if (!valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
           const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -996,15 +991,23 @@ __global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const 
           }
           if (cur >= 0) atomicAdd(&a.aggB[(size_t)cur * D + c], sum);
         }
+        if (hp == 1 && gt < 128) {
+          int* nb_ = idxb + (buf ^ 1) * 384;
+          nb_[gt] = nia, nb_[128 + gt] = nib, nb_[256 + gt] = nic;
+        }
         gbar(g);
       }
     } else {
       if (valid) {
-        float4* po = reinterpret_cast<float4*>(a.ang_out + (size_t)(r0 + r) * D + c0);
+        float4* po = reinterpret_cast<float4*>(a.ang_out);
 #pragma unroll
         for (int i = 0; i < 8; i++)
-          po[i] = make_float4(angv[4 * i] + mv[4 * i], angv[4 * i + 1] + mv[4 * i + 1], angv[4 * i + 2] + mv[4 * i + 2],
+          po[tl4<16>(t, r, c0 + 4 * i)] = make_float4(angv[4 * i] + mv[4 * i], angv[4 * i + 1] + mv[4 * i + 1], angv[4 * i + 2] + mv[4 * i + 2],
                               angv[4 * i + 3] + mv[4 * i + 3]);
+      }
+      if (gt < 128) {
+        int* nb_ = idxb + (buf ^ 1) * 384;
+        nb_[gt] = nia, nb_[128 + gt] = nib, nb_[256 + gt] = nic;
       }
       gbar(g);
     }
@@ -1040,6 +1043,11 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
     for (int i = 0; i < 6; i++) mbar_init_(&mbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (gt < 128) {  // indices of my first tile (later tiles: prefetched one tile ahead inside the loop)
+    const int64_t e = (2 * (int64_t)blockIdx.x + g) * 128 + gt;
+    const bool ok = e < a.A;
+    s_a[gt] = ok ? a.a_in[e] : -1, s_b[gt] = ok ? a.a_out[e] : -1, s_c[gt] = ok ? a.a_ctr[e] : -1;
+  }
   for (int i = tid; i < 4096; i += 512) reinterpret_cast<float4*>(WAs)[i] = reinterpret_cast<const float4*>(w.WgTcan)[i];
   if (HIDDEN)
     for (int i = tid; i < 4096; i += 512) reinterpret_cast<float4*>(WBs)[i] = reinterpret_cast<const float4*>(w.W2Tcan)[i];
@@ -1054,41 +1062,29 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
   uint32_t phase = 0;
 
   const int64_t ntiles = (a.A + 127) / 128;
-  for (int64_t t = 2 * (int64_t)blockIdx.x + g; t < ntiles; t += 2 * (int64_t)gridDim.x) {
+  const int64_t tstride = 2 * (int64_t)gridDim.x;
+  int* idxb = s_a;  // [2][a | b | c][128]
+  int buf = 0;
+  for (int64_t t = 2 * (int64_t)blockIdx.x + g; t < ntiles; t += tstride, buf ^= 1) {
     const int64_t r0 = t * 128;
     const int nvalid = (int)min((int64_t)128, a.A - r0);
-    if (gt < 128) {
-      int ia = -1, ib = -1, ic = -1;
-      if (gt < nvalid) {
-        ia = a.a_in[r0 + gt];
-        ib = a.a_out[r0 + gt];
-        ic = a.a_ctr[r0 + gt];
-      }
-      s_a[gt] = ia;
-      s_b[gt] = ib;
-      s_c[gt] = ic;
-    }
-    if (w.l2pf) {
-      const int64_t tn = t + 2 * (int64_t)gridDim.x;
-      if (tn < ntiles) {
+    const int64_t tn = t + tstride;
+    s_a = idxb + buf * 384, s_b = s_a + 128, s_c = s_a + 256;
+    int nia = -1, nib = -1, nic = -1;  // indices of my next tile, published at the end of this one
+    if (tn < ntiles && gt < 128 && tn * 128 + gt < a.A) nia = a.a_in[tn * 128 + gt], nib = a.a_out[tn * 128 + gt], nic = a.a_ctr[tn * 128 + gt];
+    if (tn < ntiles) {
+      // my next tile's adjoint rows: one contiguous 32 KB block (tile-interleaved layout), DRAM -> L2 now
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.gang + tn * (128 * 64)) + gt * 128));
+      if (w.l2pf) {
         l2_prefetch(a.uv + tn * (128 * 128), 128 * 128 * 4, gt, 256);
         if (HIDDEN) l2_prefetch(a.ds + tn * (128 * 128), 128 * 128 * 4, gt, 256);
-        if (tn * 128 + 128 <= a.A) {
-          l2_prefetch(a.gang + tn * (128 * 64), 128 * 64 * 4, gt, 256);
-          if (gt >= 128 && gt < 140) {
-            const int which = (gt - 128) >> 2, line = (gt - 128) & 3;
-            const int* base = which == 0 ? a.a_in : which == 1 ? a.a_out : a.a_ctr;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + tn * 128 + line * 32));
-          }
-        }
       }
     }
-    gbar(g);
     const bool valid = r < nvalid;
     const int ib = s_b[r];
-    const size_t row = (size_t)(valid ? r0 + r : 0);
     const float4* uv4 = reinterpret_cast<const float4*>(a.uv);
-    const float* gmrow = HIDDEN ? a.gaggB + (size_t)(valid ? ib : 0) * D : a.gang + row * D;
+    const float* gmrow = a.gaggB + (size_t)(valid && HIDDEN ? ib : 0) * D;       // HIDDEN: upstream grad of my out-bond
+    const float4* gang4 = reinterpret_cast<const float4*>(a.gang);             // !HIDDEN: my own gang row (tile-interleaved)
 #pragma unroll 1
     for (int br = 0; br < 2; br++) {
       float gp[32];
@@ -1106,7 +1102,7 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
           const int c = c0 + ch * 16 + i * 4;
           const float4 u4 = uv4[tl4<32>(t, r, c)];
           const float4 v4 = uv4[tl4<32>(t, r, 64 + c)];
-          const float4 g4 = *reinterpret_cast<const float4*>(gmrow + c);
+          const float4 g4 = HIDDEN ? *reinterpret_cast<const float4*>(gmrow + c) : gang4[tl4<16>(t, r, c)];
           const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
           for (int j = 0; j < 4; j++) {
@@ -1247,10 +1243,10 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
     {
       // gang += (accumulated gpre . Wg): the read half of the read-modify-write is issued BEFORE waiting for the
       // last GEMM (nobody else touches these 32 floats of this row during the kernel), so its latency hides behind it
-      float4* pg = reinterpret_cast<float4*>(a.gang + row * D + c0);
+      float4* pg = reinterpret_cast<float4*>(a.gang);
       float4 o[8];
 #pragma unroll
-      for (int i = 0; i < 8; i++) o[i] = valid ? pg[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; i++) o[i] = valid ? pg[tl4<16>(t, r, c0 + 4 * i)] : make_float4(0.f, 0.f, 0.f, 0.f);
       mbar_wait_(&mbar[3], phase);
       tc_fence_after();
 #pragma unroll
@@ -1264,12 +1260,16 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
             float4 x = o[ch * 4 + i];
             x.x += __uint_as_float(v[4 * i]), x.y += __uint_as_float(v[4 * i + 1]);
             x.z += __uint_as_float(v[4 * i + 2]), x.w += __uint_as_float(v[4 * i + 3]);
-            pg[ch * 4 + i] = x;
+            pg[tl4<16>(t, r, c0 + ch * 16 + 4 * i)] = x;
           }
         }
       }
     }
     phase ^= 1;
+    if (gt < 128) {
+      int* nb_ = idxb + (buf ^ 1) * 384;
+      nb_[gt] = nia, nb_[128 + gt] = nib, nb_[256 + gt] = nic;
+    }
     tc_fence_before();
     gbar(g);
   }
