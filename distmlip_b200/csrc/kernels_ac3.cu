@@ -385,8 +385,9 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_fwd_v3(const AtomConvArgs a
 //     columns of its row), turned into gpre = silu'(pre) * ghid in place once the tensor core has delivered ghid, and the
 //     SAME tile is then the scatter staging ([128][68], 16-byte LDS): no separate scatter buffer, no 32 live registers
 //     across the tensor-core waits;
-//   * branch order G, L: the second branch's first 16 columns are computed while the tensor core still multiplies the
-//     first branch, and the first branch's scatter runs while it multiplies the second;
+//   * the saved u | v are read ONCE: both second-layer gradients come out of one pass (sigmoid(u), sigmoid(v) from one
+//     reciprocal), gv goes to the tensor core at once and gu waits in registers; the layer branch's silu' is computed
+//     while the tensor core multiplies the gate branch, and the gate branch's scatter runs while it multiplies the layers;
 //   * dE/dd through the radial first-layer term, sum_j gpre[j] (M dbe)[j], takes M dbe from one more K = 16 tensor-core
 //     product (dbe . M^T) instead of a 9-term dot per column: no row-major copy of M in shared memory (the budget is
 //     W2^T 64 KB + M 16 KB + 4 stages 136 KB of 227 KB) and 27 % fewer instructions.
@@ -408,12 +409,8 @@ struct Ac3BwdSmem {
 };
 static_assert(Ac3BwdSmem::bytes <= 232448, "shared memory budget");
 
-// one branch of the backward for 16 columns: first-layer derivative parked in the stage, second-layer gradient -> hi/lo
-template <int BR>
-__device__ __forceinline__ void ac3_bwd16(uint32_t taddr, float* Ast, const float4 (&cv)[4], const float* Qrow,
-                                          const float4* uv4, size_t uvo, const float* gmrow, const float* wabW, int c,
-                                          const float (&bek)[9], const float (&dbek)[9], float& gdpart,
-                                          uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+// 16 columns of silu'(first-layer pre-activation), parked IN PLACE of the staged A half row they were computed from
+__device__ __forceinline__ void ac3_ds16(uint32_t taddr, float* Ast, const float4 (&cv)[4], const float* Qrow) {
   uint32_t v[16];
   tmem_ld16(taddr, v);
   float4 av[4];
@@ -428,22 +425,25 @@ __device__ __forceinline__ void ac3_bwd16(uint32_t taddr, float* Ast, const floa
       v[4 * i + 2] = __float_as_uint(x.z), v[4 * i + 3] = __float_as_uint(x.w);
     }
   }
-  const uint64_t kS = pk2(kNegLog2e, kNegLog2e), kOne = pk2(1.f, 1.f);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    // silu'(p) = s (1 + p (1 - s)),  s = sigmoid(p)
-    const uint64_t p01 = add2(add2(pk2(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), pk2(av[i].x, av[i].y)), pk2(cv[i].x, cv[i].y));
-    const uint64_t p23 = add2(add2(pk2(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), pk2(av[i].z, av[i].w)), pk2(cv[i].z, cv[i].w));
-    float t0, t1, t2, t3, d0, d1, d2, d3;
-    upk2(mul2(p01, kS), t0, t1), upk2(mul2(p23, kS), t2, t3);
-    upk2(add2(pk2(ex2_(t0), ex2_(t1)), kOne), d0, d1), upk2(add2(pk2(ex2_(t2), ex2_(t3)), kOne), d2, d3);
-    const uint64_t s01 = pk2(rcp_(d0), rcp_(d1)), s23 = pk2(rcp_(d2), rcp_(d3));
-    const uint64_t ds01 = mul2(s01, fma2(p01, sub2(kOne, s01), kOne)), ds23 = mul2(s23, fma2(p23, sub2(kOne, s23), kOne));
-    float x0, x1, x2, x3;
-    upk2(ds01, x0, x1), upk2(ds23, x2, x3);
-    *reinterpret_cast<float4*>(Ast + 4 * i) = make_float4(x0, x1, x2, x3);
+    const float a4[4] = {av[i].x, av[i].y, av[i].z, av[i].w}, c4[4] = {cv[i].x, cv[i].y, cv[i].z, cv[i].w};
+    float d[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float p = (__uint_as_float(v[4 * i + j]) + a4[j]) + c4[j];
+      const float sg = rcp_(1.f + ex2_(p * kNegLog2e));
+      d[j] = sg * (1.f + p * (1.f - sg));  // silu'(p)
+    }
+    *reinterpret_cast<float4*>(Ast + 4 * i) = make_float4(d[0], d[1], d[2], d[3]);
   }
-  // gradient w.r.t. this branch's second-layer pre-activation (gu for BR == 0, gv for BR == 1)
+}
+
+// second-layer gradients of 16 columns from ONE pass over the saved u | v: gv (gate branch) -> tf32 hi / lo for the tensor
+// core now, gu (layer branch) kept in fp32 for the second product; dE/dd through the shared bond weights w_ab
+__device__ __forceinline__ void ac3_second16(const float4* uv4, size_t uvo, const float* gmrow, const float* wabW, int c,
+                                             const float (&bek)[9], const float (&dbek)[9], float& gdpart, float* gu,
+                                             uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const float4 u4 = uv4[uvo + (size_t)i * 128];
@@ -452,24 +452,20 @@ __device__ __forceinline__ void ac3_bwd16(uint32_t taddr, float* Ast, const floa
     const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
     float wab4[4], wabp4[4];
     radial_dot4(wabW, c + 4 * i, bek, wab4);
-    if (BR == 0) radial_dot4(wabW, c + 4 * i, dbek, wabp4);
+    radial_dot4(wabW, c + 4 * i, dbek, wabp4);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       // sigmoid(u), sigmoid(v) from ONE reciprocal; the exponentials are clamped so that the product stays finite
       const float eu = fminf(ex2_(uu[j] * kNegLog2e), 1e18f), ev = fminf(ex2_(vv[j] * kNegLog2e), 1e18f);
       const float rr = rcp_((1.f + eu) * (1.f + ev));
       const float su = rr * (1.f + ev), sv = rr * (1.f + eu);
-      const float oL = uu[j] * su;
-      float gq;
-      if (BR == 0) {
-        gq = gg[j] * sv * wab4[j] * (su * (1.f + uu[j] * (1.f - su)));
-        gdpart = fmaf(gg[j] * oL * sv, wabp4[j], gdpart);
-      } else {
-        gq = gg[j] * oL * wab4[j] * sv * (1.f - sv);
-      }
-      const uint32_t h = tf32_hi_bits(gq);
+      const float oL = uu[j] * su, gw = gg[j] * wab4[j];
+      gu[4 * i + j] = gw * sv * (su * (1.f + uu[j] * (1.f - su)));
+      gdpart = fmaf(gg[j] * oL * sv, wabp4[j], gdpart);
+      const float gv = gw * oL * sv * (1.f - sv);
+      const uint32_t h = tf32_hi_bits(gv);
       hi[4 * i + j] = h;
-      lo[4 * i + j] = __float_as_uint(gq - __uint_as_float(h));
+      lo[4 * i + j] = __float_as_uint(gv - __uint_as_float(h));
     }
   }
 }
@@ -626,20 +622,22 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_bwd_v3(const AtomConvArgs a
 #pragma unroll
     for (int i = 0; i < 4; i++) cv0[i] = *reinterpret_cast<const float4*>(Crow + 64 + 4 * i);
 
-    // ---------------- gate branch: silu'(pre) -> stage0, gv -> H ----------------
+    // ---------------- first-layer derivatives of the gate branch -> stage0 (in place) ----------------
     mbar_wait_(&mbar[6], phase);
     mbar_wait_(&mbar[0], phase);
     tc_fence_after();
+    ac3_ds16(tlane + COL_D + 64 + c0, stage0 + r * PITCH + c0, cv0, viaQ ? Qrow + 64 : nullptr);
+#pragma unroll
+    for (int i = 0; i < 4; i++) cv1[i] = *reinterpret_cast<const float4*>(Crow + 64 + 16 + 4 * i);  // same line as cv0: L1
+    ac3_ds16(tlane + COL_D + 64 + c0 + 16, stage0 + r * PITCH + c0 + 16, cv1, viaQ ? Qrow + 64 + 16 : nullptr);
+    // ---------------- second layers: one pass over the saved u | v; gv -> H now, gu parked in registers ----------------
+    float gu[32];
     {
       uint32_t hi[16], lo[16];
-      ac3_bwd16<1>(tlane + COL_D + 64 + c0, stage0 + r * PITCH + c0, cv0, viaQ ? Qrow + 64 : nullptr, uv4, uvo, gmrow, wabW, c0,
-                   bek, dbek, gdpart, hi, lo);
+      ac3_second16(uv4, uvo, gmrow, wabW, c0, bek, dbek, gdpart, gu, hi, lo);
       tmem_st16(tlane + COL_H + c0, hi);
       tmem_st16(tlane + COL_H + 64 + c0, lo);
-#pragma unroll
-      for (int i = 0; i < 4; i++) cv1[i] = *reinterpret_cast<const float4*>(Crow + 64 + 16 + 4 * i);  // same line as cv0: L1
-      ac3_bwd16<1>(tlane + COL_D + 64 + c0 + 16, stage0 + r * PITCH + c0 + 16, cv1, viaQ ? Qrow + 64 + 16 : nullptr, uv4,
-                   uvo + 4 * 128, gmrow + 16, wabW, c0 + 16, bek, dbek, gdpart, hi, lo);
+      ac3_second16(uv4, uvo + 4 * 128, gmrow + 16, wabW, c0 + 16, bek, dbek, gdpart, gu + 16, hi, lo);
       tmem_st16(tlane + COL_H + c0 + 16, hi);
       tmem_st16(tlane + COL_H + 64 + c0 + 16, lo);
     }
@@ -678,22 +676,25 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_bwd_v3(const AtomConvArgs a
       umma_commit(&mbar[1]);
     }
 
-    // ---------------- layer branch: silu'(pre) -> stage1, gu -> H ----------------
+    // ---------------- first-layer derivatives of the layer branch -> stage1, while the tensor core multiplies ----------------
     mbar_wait_(&mbar[7], phase);
-    {
-      uint32_t hi[16], lo[16];
-      ac3_bwd16<0>(tlane + COL_D + c0, stage1 + r * PITCH + c0, cv0, viaQ ? Qrow : nullptr, uv4, uvo, gmrow, wabW, c0, bek, dbek,
-                   gdpart, hi, lo);
-      mbar_wait_(&mbar[1], phase);  // GEMM3 (gates) done: H is free, ghid of the gate branch is in D[:, 64..127]
-      tc_fence_after();
-      tmem_st16(tlane + COL_H + c0, hi);
-      tmem_st16(tlane + COL_H + 64 + c0, lo);
+    ac3_ds16(tlane + COL_D + c0, stage1 + r * PITCH + c0, cv0, viaQ ? Qrow : nullptr);
 #pragma unroll
-      for (int i = 0; i < 4; i++) cv1[i] = *reinterpret_cast<const float4*>(Crow + 16 + 4 * i);
-      ac3_bwd16<0>(tlane + COL_D + c0 + 16, stage1 + r * PITCH + c0 + 16, cv1, viaQ ? Qrow + 16 : nullptr, uv4, uvo + 4 * 128,
-                   gmrow + 16, wabW, c0 + 16, bek, dbek, gdpart, hi, lo);
-      tmem_st16(tlane + COL_H + c0 + 16, hi);
-      tmem_st16(tlane + COL_H + 64 + c0 + 16, lo);
+    for (int i = 0; i < 4; i++) cv1[i] = *reinterpret_cast<const float4*>(Crow + 16 + 4 * i);
+    ac3_ds16(tlane + COL_D + c0 + 16, stage1 + r * PITCH + c0 + 16, cv1, viaQ ? Qrow + 16 : nullptr);
+    mbar_wait_(&mbar[1], phase);  // GEMM3 (gates) done: H is free, ghid of the gate branch is in D[:, 64..127]
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const uint32_t h = tf32_hi_bits(gu[ch * 16 + i]);
+        hi[i] = h;
+        lo[i] = __float_as_uint(gu[ch * 16 + i] - __uint_as_float(h));
+      }
+      tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
+      tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
     }
     tc_wait_st();
     tc_fence_before();
