@@ -170,6 +170,8 @@ struct b2m_engine {
   std::map<const float*, const float*> canon_of;  // FFMA-layout GEMM operand -> canonical tcgen05 copy
   int num_sms = 148;
   bool use_tc = true;  // tcgen05 kernels; B2M_LEGACY_FFMA=1 selects the FP32-FFMA tile kernels (A/B checks)
+  bool debug_no_halo = false;  // B2M_DEBUG_NO_HALO=1: a b2m_set_partition view may run with its exchanges skipped (wrong
+                               // numbers, right amount of per-partition work: timing one slab of an N-way split on one GPU)
   int ac_gen = 3;      // atom-conv kernel generation on the tcgen05 path: 3 (default, kernels_ac3.cu), 1 = first generation,
                        // 4 = third-generation forward with the first-generation backward (B2M_ATOMCONV, A/B checks)
 };
@@ -562,7 +564,7 @@ static cudaEvent_t next_halo_event(b2m_engine* e) {
 //   halo_forward_begin: [compute: producer done] -> [comm stream: pack, send / receive or peer stores]
 //   halo_forward_end  : compute stream waits for the exchange (and, in a group, for the neighbours' stores)
 static void halo_forward_begin(b2m_engine* e, bool bonds, int l) {
-  if (e->world <= 1) return;
+  if (e->world <= 1 || e->debug_no_halo) return;
   Graph& g = e->g;
   float* buf = halo_buffer(e, bonds, l);
   const int* nto = bonds ? g.nb_to : g.n_to;
@@ -602,7 +604,7 @@ static void halo_forward_begin(b2m_engine* e, bool bonds, int l) {
   B2M_CK(cudaEventRecord(e->ev_halo, e->cst));
 }
 static void halo_forward_end(b2m_engine* e) {
-  if (e->world <= 1) return;
+  if (e->world <= 1 || e->debug_no_halo) return;
   if (e->leader != nullptr) {
     b2m_engine* L = e->leader;
     const int k = e->hpoint++;
@@ -615,7 +617,7 @@ static void halo_forward_end(b2m_engine* e) {
 }
 // backward: my halo rows of the adjoint -> owners (accumulate), then zero the halo rows
 static void halo_backward(b2m_engine* e, float* gbuf, bool bonds) {
-  if (e->world <= 1) return;
+  if (e->world <= 1 || e->debug_no_halo) return;
   Graph& g = e->g;
   const int* nto = bonds ? g.nb_to : g.n_to;
   const int* toff = bonds ? g.bto_off : g.to_off;
@@ -906,7 +908,7 @@ static void backward(b2m_engine* e) {
 static void run(b2m_engine* e, bool grads) {
   B2M_REQUIRE(e->finalized, B2M_ERR_STATE, "weights not finalized");
   B2M_REQUIRE(e->have_graph, B2M_ERR_STATE, "b2m_set_structure has not been called");
-  B2M_REQUIRE(e->world == 1 || e->comm != nullptr || e->leader != nullptr, B2M_ERR_STATE,
+  B2M_REQUIRE(e->world == 1 || e->comm != nullptr || e->leader != nullptr || e->debug_no_halo, B2M_ERR_STATE,
               "world > 1 without a communicator (b2m_set_partition is a graph-only view)");
   e->hpoint = 0;
   for (auto& p : e->gather_ev) {
@@ -920,7 +922,7 @@ static void run(b2m_engine* e, bool grads) {
   forward(e);
   B2M_CK(cudaEventRecord(e->ev[1], e->st));
   if (grads) backward(e);
-  if (e->world > 1 && e->leader == nullptr) {
+  if (e->world > 1 && e->leader == nullptr && !e->debug_no_halo) {
     NCCL_CK(g_nccl.AllReduce(e->scal.p, e->scal.p, 10, ncclFloat64, ncclSum, e->comm, e->st));
     if (grads)
       NCCL_CK(g_nccl.AllReduce(e->forces.p, e->forces.p, (size_t)e->g.N * 3, ncclFloat32, ncclSum, e->comm, e->st));
@@ -1078,6 +1080,8 @@ static b2m_engine* create_one(const b2m_model_desc* desc, int device, int count)
     e->use_tc = !(leg && leg[0] == '1');
     const char* gen = getenv("B2M_ATOMCONV");
     e->ac_gen = gen ? atoi(gen) : 3;
+    const char* nh = getenv("B2M_DEBUG_NO_HALO");
+    e->debug_no_halo = nh && nh[0] == '1';
     B2M_CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     B2M_CK(cudaStreamCreateWithFlags(&e->cst, cudaStreamNonBlocking));
     B2M_CK(cudaEventCreateWithFlags(&e->ev_prod, cudaEventDisableTiming));
