@@ -156,17 +156,11 @@ class Engine:
 
     # ---- structure / compute ----
     def set_structure(self, cart, lattice, species, pbc, tol=1e-8):
+        """positions [n,3] f64 and species [n] i32 are handed to the library as they are (no copy when already contiguous
+        in that dtype): it stages them through its own page-locked buffer with several copy threads"""
+        cart = np.ascontiguousarray(cart, dtype=np.float64)
+        species = np.ascontiguousarray(species, dtype=np.int32)
         n = len(cart)
-        if getattr(self, "_pin_n", 0) < n:  # page-locked staging buffers (async H2D inside the library)
-            import torch
-
-            self._pin_cart = torch.empty(n * 3, dtype=torch.float64).pin_memory().numpy()
-            self._pin_spec = torch.empty(n, dtype=torch.int32).pin_memory().numpy()
-            self._pin_n = n
-        pc, ps = self._pin_cart[: n * 3].reshape(n, 3), self._pin_spec[:n]
-        np.copyto(pc, np.asarray(cart, dtype=np.float64))
-        np.copyto(ps, np.asarray(species, dtype=np.int32))
-        cart, species = pc, ps
         lattice = np.ascontiguousarray(lattice, dtype=np.float64).reshape(9)
         pbc = np.ascontiguousarray(pbc, dtype=np.int32)
         self.natoms = n

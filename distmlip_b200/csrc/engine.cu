@@ -146,6 +146,12 @@ struct b2m_engine {
   int hpoint = 0;
   DBuf<float> precv[2];            // adjoint rows pushed by my neighbours (backward), double-buffered by point parity
   DBuf<float> ftmp;                // leader: staging of a peer's force array
+  // page-locked staging owned by the library: host arrays go through it with a few copy threads (a single-threaded
+  // memcpy of 24 MB of positions was the largest host item of an end-to-end step at 1 M atoms)
+  void* pin_in = nullptr;   // [N,3] f64 positions followed by [N] i32 species
+  size_t pin_in_cap = 0;
+  void* pin_out = nullptr;  // [N,3] f32 forces
+  size_t pin_out_cap = 0;
   // graph + workspace
   Graph g;
   bool have_graph = false;
@@ -944,6 +950,32 @@ static void run(b2m_engine* e, bool grads) {
   e->t_total = e->t_fwd + e->t_bwd;
 }
 
+// parallel host copy (page-locked <-> pageable): a handful of threads saturate the host memory system, one does not
+static void par_memcpy(void* dst, const void* src, size_t bytes) {
+  const size_t kMin = 4u << 20;
+  unsigned nt = (unsigned)std::min<size_t>(4, bytes / kMin);
+  if (nt <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t chunk = (bytes / nt + 4095) & ~(size_t)4095;
+  for (unsigned t = 0; t < nt; t++) {
+    const size_t o = (size_t)t * chunk;
+    if (o >= bytes) break;
+    const size_t n = std::min(chunk, bytes - o);
+    th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, n); });
+  }
+  for (auto& x : th) x.join();
+}
+static void ensure_pinned(void*& p, size_t& cap, size_t bytes) {
+  if (bytes <= cap) return;
+  if (p) cudaFreeHost(p);
+  p = nullptr, cap = 0;
+  B2M_CK(cudaHostAlloc(&p, bytes + bytes / 8, cudaHostAllocDefault));
+  cap = bytes + bytes / 8;
+}
+
 __global__ void k_add_inplace(int64_t n, const float* __restrict__ src, float* __restrict__ dst) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
@@ -1008,9 +1040,13 @@ static void fetch(b2m_engine* e, double* energy, float* forces, float* stress9) 
       B2M_CK(cudaGetLastError());
     }
   }
-  if (forces)
-    B2M_CK(cudaMemcpyAsync(forces, e->forces.p, (size_t)e->g.N * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  const size_t fbytes = (size_t)e->g.N * 3 * sizeof(float);
+  if (forces) {
+    ensure_pinned(e->pin_out, e->pin_out_cap, fbytes);
+    B2M_CK(cudaMemcpyAsync(e->pin_out, e->forces.p, fbytes, cudaMemcpyDeviceToHost, e->st));
+  }
   B2M_CK(cudaStreamSynchronize(e->st));
+  if (forces) par_memcpy(forces, e->pin_out, fbytes);
   for (size_t p = 1; p < e->parts.size(); p++) {  // energy and virial of the other partitions
     double ps[10];
     b2m_engine* pe = e->parts[p];
@@ -1151,6 +1187,8 @@ static void destroy_one(b2m_engine* h) {
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->hev) cudaEventDestroy(ev);
+  if (h->pin_in) cudaFreeHost(h->pin_in);
+  if (h->pin_out) cudaFreeHost(h->pin_out);
   if (h->ev_prod) cudaEventDestroy(h->ev_prod);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
   if (h->cst) cudaStreamDestroy(h->cst);
@@ -1257,6 +1295,15 @@ int b2m_set_partition(b2m_handle h, int rank, int world) {
 static void set_structure_one(b2m_engine* h, int64_t natoms, const double* cart, const double* lattice9,
                               const int32_t* species, const int* pbc3, double tol) {
   h->have_graph = false;
+  // positions and species through the library's page-locked staging (asynchronous upload inside the build)
+  if (natoms > 0 && natoms < (1LL << 31) / 4) {
+    const size_t cb = (size_t)natoms * 3 * sizeof(double), sb = (size_t)natoms * sizeof(int32_t);
+    ensure_pinned(h->pin_in, h->pin_in_cap, cb + sb);
+    par_memcpy(h->pin_in, cart, cb);
+    memcpy((char*)h->pin_in + cb, species, sb);
+    cart = reinterpret_cast<const double*>(h->pin_in);
+    species = reinterpret_cast<const int32_t*>((const char*)h->pin_in + cb);
+  }
   B2M_CK(cudaEventRecord(h->ev[3], h->st));
   h->g.build(h->st, natoms, cart, lattice9, species, pbc3, h->desc.cutoff, h->desc.three_body_cutoff, tol, h->rank,
              h->world);
