@@ -177,7 +177,9 @@ def best_thread_count(n_cells=8):
     (up to every host core) on the SAME sample size the baseline is then timed on, so the CPU arm is not handicapped
     on many-core hosts.  Returns (threads, {threads: seconds})."""
     cores = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}) or [cores]
+    # (beyond 64 threads these small tensors get dramatically slower -- 36-52 s per step at 128 threads on the bench host,
+    #  profiles/r02j, r02r -- so the probe stops there instead of spending a minute to confirm it)
+    cands = sorted({c for c in (8, 16, 32, 64) if c <= cores}) or [cores]
     best, best_t, seen = cands[0], 1e30, {}
     cpu_reference_step(n_cells, cands[0])  # first call pays imports / allocator warm-up
     for c in cands:
