@@ -281,17 +281,17 @@ __device__ __forceinline__ AngleGeom angle_geom(const float4 a, const float4 b) 
   return g;
 }
 
-// ang0[r][c] = sum_k fourier_k(theta_r) Wae[c][k]      (32 angles per block)
+// ang0[r][c] = sum_k fourier_k(theta_r) Wae[c][k]      (128 angles per block = one tile of the interleaved layout)
 __global__ void __launch_bounds__(256) k_angle_init(int64_t na, const int* __restrict__ a_in,
                                                     const int* __restrict__ a_out, const float4* __restrict__ b_vec,
                                                     const float* __restrict__ fa, const float* __restrict__ Wae,
                                                     float* __restrict__ ang0, int il) {
-  __shared__ float f_s[32][12];
+  __shared__ float f_s[128][12];
   __shared__ float Ws[64 * 9];
-  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int64_t r0 = (int64_t)blockIdx.x * 128;
   const int tid = threadIdx.x;
   for (int i = tid; i < 576; i += 256) Ws[i] = Wae[i];
-  if (tid < 32) {
+  if (tid < 128) {
     const int64_t r = r0 + tid;
     if (r < na) {
       const AngleGeom g = angle_geom(b_vec[a_in[r]], b_vec[a_out[r]]);
@@ -308,19 +308,26 @@ __global__ void __launch_bounds__(256) k_angle_init(int64_t na, const int* __res
     }
   }
   __syncthreads();
-  for (int i = tid; i < 32 * 64; i += 256) {
-    const int r = i >> 6, c = i & 63;
+  for (int i = tid; i < 16 * 128; i += 256) {  // (4 columns, row): consecutive lanes = consecutive rows
+    const int cq = i >> 7, r = i & 127;
     if (r0 + r >= na) continue;
-    float s = 0.f;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < 9; k++) s = fmaf(f_s[r][k], Ws[c * 9 + k], s);
-    ang0[ang_index(r0 + r, c, il)] = s;
+    for (int k = 0; k < 9; k++) {
+      const float f = f_s[r][k];
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = fmaf(f, Ws[(4 * cq + j) * 9 + k], v[j]);
+    }
+    if (il)
+      reinterpret_cast<float4*>(ang0)[(size_t)blockIdx.x * 16 * 128 + i] = make_float4(v[0], v[1], v[2], v[3]);
+    else
+      *reinterpret_cast<float4*>(ang0 + (size_t)(r0 + r) * 64 + 4 * cq) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 void launch_angle_init(cudaStream_t st, int64_t na, const int* a_in, const int* a_out, const float4* b_vec,
                        const float* fa, const float* Wae, float* ang0, bool interleaved) {
   if (na <= 0) return;
-  k_angle_init<<<cdiv(na, 32), 256, 0, st>>>(na, a_in, a_out, b_vec, fa, Wae, ang0, interleaved ? 1 : 0);
+  k_angle_init<<<cdiv(na, 128), 256, 0, st>>>(na, a_in, a_out, b_vec, fa, Wae, ang0, interleaved ? 1 : 0);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
@@ -1042,18 +1049,23 @@ void launch_line_bwd(cudaStream_t st, const LineArgs& a, bool hidden) {
 // ============================================================================================
 // bond update (node-level, after the W_out GEMM):  h' = h + upd * w3b(d_b)
 // ============================================================================================
+// 128 bonds per block, 16-byte accesses: these are pure streaming kernels (300 MB per launch at 97 k atoms) and ran at a
+// third of the HBM rate with 32 bonds per block and 4-byte accesses (profiles/r02k_kernel_shares_97k.txt)
+constexpr int BNR = 128;  // bonds per block
 template <int MODE>  // 0: fwd, 1: bwd (gupd, gdb), 2: h0 backward (gdb only)
 __global__ void __launch_bounds__(256) k_bond_node(int nb, const float4* __restrict__ b_vec, RadialParams rp,
                                                    const float* __restrict__ W /*[64][9]*/,
                                                    const float* __restrict__ x0 /*h | gh | gh0*/,
                                                    const float* __restrict__ x1 /*upd*/, float* __restrict__ out,
                                                    float* __restrict__ gdb) {
-  __shared__ float be_s[32][12], dbe_s[32][12], gk_s[32][12];
-  __shared__ float Ws[64 * 9];
-  __shared__ float P[32][65];  // MODE 1: gh*upd, MODE 2: gh0 (staged once, coalesced)
-  const int b0 = blockIdx.x * 32, tid = threadIdx.x;
+  extern __shared__ float bn_smem[];
+  float(*be_s)[12] = reinterpret_cast<float(*)[12]>(bn_smem);                 // [BNR][12]
+  float(*dbe_s)[12] = reinterpret_cast<float(*)[12]>(bn_smem + BNR * 12);     // [BNR][12]
+  float* Ws = bn_smem + 2 * BNR * 12;                                         // [64][9]
+  float(*P)[68] = reinterpret_cast<float(*)[68]>(bn_smem + 2 * BNR * 12 + 576);  // [BNR][68]  MODE 1: gh*upd, MODE 2: gh0
+  const int b0 = blockIdx.x * BNR, tid = threadIdx.x;
   for (int i = tid; i < 576; i += 256) Ws[i] = W[i];
-  for (int i = tid; i < 32 * 9; i += 256) {
+  for (int i = tid; i < BNR * 9; i += 256) {
     const int r = i / 9, k = i % 9;
     float be = 0.f, dbe = 0.f;
     if (b0 + r < nb) rbf_env_k(b_vec[b0 + r].w, rp.freq[k], rp, be, dbe);
@@ -1061,87 +1073,107 @@ __global__ void __launch_bounds__(256) k_bond_node(int nb, const float4* __restr
     dbe_s[r][k] = dbe;
   }
   __syncthreads();
-  for (int i = tid; i < 32 * 64; i += 256) {
-    const int r = i >> 6, c = i & 63;
-    float pv = 0.f;
+  for (int i = tid; i < BNR * 16; i += 256) {  // (row, 4 columns) per item
+    const int r = i >> 4, c = (i & 15) * 4;
+    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (b0 + r < nb) {
       const size_t o = (size_t)(b0 + r) * 64 + c;
-      const float a0 = x0[o];
+      const float4 a0 = *reinterpret_cast<const float4*>(x0 + o);
       if (MODE == 2) {
         pv = a0;
       } else {
-        float w = 0.f;
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < 9; k++) w = fmaf(be_s[r][k], Ws[c * 9 + k], w);
-        const float a1 = x1[o];
+        for (int k = 0; k < 9; k++) {
+          const float b = be_s[r][k];
+#pragma unroll
+          for (int j = 0; j < 4; j++) w[j] = fmaf(b, Ws[(c + j) * 9 + k], w[j]);
+        }
+        const float4 a1 = *reinterpret_cast<const float4*>(x1 + o);
         if (MODE == 0) {
-          out[o] = a0 + a1 * w;
+          *reinterpret_cast<float4*>(out + o) = make_float4(a0.x + a1.x * w[0], a0.y + a1.y * w[1], a0.z + a1.z * w[2], a0.w + a1.w * w[3]);
         } else {
-          out[o] = a0 * w;
-          pv = a0 * a1;
+          *reinterpret_cast<float4*>(out + o) = make_float4(a0.x * w[0], a0.y * w[1], a0.z * w[2], a0.w * w[3]);
+          pv = make_float4(a0.x * a1.x, a0.y * a1.y, a0.z * a1.z, a0.w * a1.w);
         }
       }
     }
-    if (MODE != 0) P[r][c] = pv;
+    if (MODE != 0) *reinterpret_cast<float4*>(&P[r][c]) = pv;
   }
   if (MODE == 1 || MODE == 2) {
     __syncthreads();
-    // gk[r][k] = sum_c P[r][c] W[c][k];  gdb[r] += sum_k gk dbe_k
-    for (int i = tid; i < 32 * 9; i += 256) {
-      const int r = i / 9, k = i % 9;
-      float s = 0.f;
+    // gdb[r] += sum_k (sum_c P[r][c] W[c][k]) dbe_k : two threads per bond (k parity), partial sums combined by shuffle
+    {
+      const int r = tid >> 1, par = tid & 1;
+      float tot = 0.f;
+      for (int k = par; k < 9; k += 2) {
+        float sacc = 0.f;
 #pragma unroll 8
-      for (int c = 0; c < 64; c++) s = fmaf(P[r][c], Ws[c * 9 + k], s);
-      gk_s[r][k] = s * dbe_s[r][k];
-    }
-    __syncthreads();
-    if (tid < 32 && b0 + tid < nb) {
-      float s = 0.f;
-      for (int k = 0; k < 9; k++) s += gk_s[tid][k];
-      gdb[b0 + tid] += s;
+        for (int c = 0; c < 64; c++) sacc = fmaf(P[r][c], Ws[c * 9 + k], sacc);
+        tot += sacc * dbe_s[r][k];
+      }
+      tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+      if (par == 0 && b0 + r < nb) gdb[b0 + r] += tot;
     }
   }
+}
+constexpr size_t kBondNodeSmem = (size_t)(2 * BNR * 12 + 576 + BNR * 68) * sizeof(float);
+template <int MODE>
+static void launch_bond_node(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp, const float* W, const float* x0,
+                             const float* x1, float* out, float* gdb) {
+  static PerDeviceOnce attr;
+  if (auto once_ = attr.first(); once_)
+    B2M_CK(cudaFuncSetAttribute(k_bond_node<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBondNodeSmem));
+  k_bond_node<MODE><<<cdiv(nb, BNR), 256, kBondNodeSmem, st>>>(nb, b_vec, rp, W, x0, x1, out, gdb);
+  B2M_CK(cudaGetLastError());
+  g_launch_count++;
 }
 void launch_bond_update_fwd(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp3, const float* W3bw,
                             const float* h, const float* upd, float* hout) {
   if (nb <= 0) return;
-  k_bond_node<0><<<cdiv(nb, 32), 256, 0, st>>>(nb, b_vec, rp3, W3bw, h, upd, hout, nullptr);
-  B2M_CK(cudaGetLastError());
-  g_launch_count++;
+  launch_bond_node<0>(st, nb, b_vec, rp3, W3bw, h, upd, hout, nullptr);
 }
 void launch_bond_update_bwd(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp3, const float* W3bw,
                             const float* gh, const float* upd, float* gupd, float* gdb) {
   if (nb <= 0) return;
-  k_bond_node<1><<<cdiv(nb, 32), 256, 0, st>>>(nb, b_vec, rp3, W3bw, gh, upd, gupd, gdb);
-  B2M_CK(cudaGetLastError());
-  g_launch_count++;
+  launch_bond_node<1>(st, nb, b_vec, rp3, W3bw, gh, upd, gupd, gdb);
 }
 void launch_h0_bwd(cudaStream_t st, int nb, const float4* b_vec, RadialParams rp, const float* Wbe, const float* gh0,
                    float* gdb) {
   if (nb <= 0) return;
-  k_bond_node<2><<<cdiv(nb, 32), 256, 0, st>>>(nb, b_vec, rp, Wbe, gh0, nullptr, nullptr, gdb);
-  B2M_CK(cudaGetLastError());
-  g_launch_count++;
+  launch_bond_node<2>(st, nb, b_vec, rp, Wbe, gh0, nullptr, nullptr, gdb);
 }
 
-// theta / Fourier backward (32 angles per block)
+// theta / Fourier backward (128 angles per block = one tile of the interleaved layout)
+constexpr int ANR = 128;
 __global__ void __launch_bounds__(256) k_angle_init_bwd(int64_t na, const int* __restrict__ a_in,
                                                         const int* __restrict__ a_out,
                                                         const float4* __restrict__ b_vec, const float* __restrict__ fa,
                                                         const float* __restrict__ Wae, const float* __restrict__ gang0,
                                                         float* __restrict__ gbvec, int il) {
-  __shared__ float gf_s[32][12];
-  __shared__ float Ws[64 * 9];
-  __shared__ float G[32][65];
-  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  extern __shared__ float ab_smem[];
+  float(*G)[65] = reinterpret_cast<float(*)[65]>(ab_smem);                  // [ANR][65]
+  float(*gf_s)[12] = reinterpret_cast<float(*)[12]>(ab_smem + ANR * 65);    // [ANR][12]
+  float* Ws = ab_smem + ANR * 65 + ANR * 12;                                // [64][9]
+  const int64_t r0 = (int64_t)blockIdx.x * ANR;
   const int tid = threadIdx.x;
   for (int i = tid; i < 576; i += 256) Ws[i] = Wae[i];
-  for (int i = tid; i < 32 * 64; i += 256) {
-    const int r = i >> 6, c = i & 63;
-    G[r][c] = (r0 + r < na) ? gang0[ang_index(r0 + r, c, il)] : 0.f;
+  if (il) {  // tile-interleaved: float4 (c/4, row) -> consecutive lanes read consecutive rows of one column group
+    const float4* g4 = reinterpret_cast<const float4*>(gang0) + (size_t)blockIdx.x * 16 * 128;
+    for (int i = tid; i < 16 * ANR; i += 256) {
+      const int cq = i >> 7, r = i & 127;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < na) v = g4[i];
+      G[r][4 * cq] = v.x, G[r][4 * cq + 1] = v.y, G[r][4 * cq + 2] = v.z, G[r][4 * cq + 3] = v.w;
+    }
+  } else {
+    for (int i = tid; i < ANR * 64; i += 256) {
+      const int r = i >> 6, c = i & 63;
+      G[r][c] = (r0 + r < na) ? gang0[(size_t)(r0 + r) * 64 + c] : 0.f;
+    }
   }
   __syncthreads();
-  for (int i = tid; i < 32 * 9; i += 256) {
+  for (int i = tid; i < ANR * 9; i += 256) {
     const int r = i / 9, k = i % 9;
     float s = 0.f;
 #pragma unroll 8
@@ -1149,7 +1181,7 @@ __global__ void __launch_bounds__(256) k_angle_init_bwd(int64_t na, const int* _
     gf_s[r][k] = s;
   }
   __syncthreads();
-  if (tid < 32 && r0 + tid < na) {
+  if (tid < ANR && r0 + tid < na) {
     const int64_t r = r0 + tid;
     const int ia = a_in[r], ib = a_out[r];
     const AngleGeom g = angle_geom(b_vec[ia], b_vec[ib]);
@@ -1175,10 +1207,14 @@ __global__ void __launch_bounds__(256) k_angle_init_bwd(int64_t na, const int* _
     }
   }
 }
+constexpr size_t kAngleBwdSmem = (size_t)(ANR * 65 + ANR * 12 + 576) * sizeof(float);
 void launch_angle_init_bwd(cudaStream_t st, int64_t na, const int* a_in, const int* a_out, const float4* b_vec,
                            const float* fa, const float* Wae, const float* gang0, float* gbvec, bool interleaved) {
   if (na <= 0) return;
-  k_angle_init_bwd<<<cdiv(na, 32), 256, 0, st>>>(na, a_in, a_out, b_vec, fa, Wae, gang0, gbvec, interleaved ? 1 : 0);
+  static PerDeviceOnce attr;
+  if (auto once_ = attr.first(); once_)
+    B2M_CK(cudaFuncSetAttribute(k_angle_init_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAngleBwdSmem));
+  k_angle_init_bwd<<<cdiv(na, ANR), 256, kAngleBwdSmem, st>>>(na, a_in, a_out, b_vec, fa, Wae, gang0, gbvec, interleaved ? 1 : 0);
   B2M_CK(cudaGetLastError());
   g_launch_count++;
 }
