@@ -16,14 +16,14 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("B2M_TEST_EXPERIMENTAL") != "1", reason="opt-in: B2M_TEST_EXPERIMENTAL=1")]
 
 SWITCHES = [
-    {"B2M_ATOMCONV": "1"},
-    {"B2M_ATOMCONV": "4"},
-    {"B2M_AC3_L1PF": "0"},
-    {"B2M_GEMM_PIPE": "0"},
+    {"B2M_ATOMCONV": "1"},                                   # first-generation atom-conv kernels (per-lane gathers)
+    {"B2M_ATOMCONV": "4"},                                   # third-generation forward + first-generation backward
+    {"B2M_AC3_L1PF": "0"},                                   # no L1 prefetch of the next tile's C rows
+    {"B2M_GEMM_PIPE": "0"},                                  # first row-GEMM kernel
     {"B2M_L2_PREFETCH": "2"},
     {"B2M_L2_PREFETCH": "0"},
-    {"B2M_FWD_PREFETCH": "0"},
-    {"B2M_FWD_THREADS": "512", "B2M_BWD_THREADS": "512"},
+    {"B2M_ATOMCONV": "1", "B2M_FWD_PREFETCH": "0"},          # generation-1 only switches
+    {"B2M_ATOMCONV": "1", "B2M_FWD_THREADS": "512", "B2M_BWD_THREADS": "512"},
 ]
 
 
