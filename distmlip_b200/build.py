@@ -57,5 +57,24 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_probes(verbose=False):
+    """standalone hardware probes under csrc/tests/ (umma_probe: tcgen05 descriptor variants; gather_probe: gather staging
+    and MUFU rates) -> csrc/build/<name>; they are what profiles/r02b_run.sh runs on the GPU box"""
+    nvcc = _nvcc()
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    outs = []
+    for name in ("umma_probe", "gather_probe"):
+        out = os.path.join(objdir, name)
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", out, os.path.join(CSRC, "tests", name + ".cu")]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    if "--probes" in sys.argv:
+        print(build_probes(verbose=True))

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (probe binaries: python -m distmlip_b200.build --probes)
 # round 2, call b: hardware facts behind the third-generation edge-gather kernels.
 #  (1) tcgen05 TF32 with an MN-major B operand over the canonical K-major image of W (-> W^T without a second copy)
 #  (2) gather staging throughput per SM: bulk copies vs per-lane LDG vs coalesced LDG+STS vs cp.async; MUFU rates
