@@ -331,8 +331,10 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_fwd_v3(const AtomConvArgs a
         float4* puv = reinterpret_cast<float4*>(a.uv_save);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          puv[tl4<32>(t, r, c0 + ch * 16 + 4 * i)] = make_float4(uu[4 * i], uu[4 * i + 1], uu[4 * i + 2], uu[4 * i + 3]);
-          puv[tl4<32>(t, r, 64 + c0 + ch * 16 + 4 * i)] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+          // streaming stores (evict-first): 512 B/edge written once here and read once by the backward must not push
+          // the gathered A / C rows out of L2
+          __stcs(&puv[tl4<32>(t, r, c0 + ch * 16 + 4 * i)], make_float4(uu[4 * i], uu[4 * i + 1], uu[4 * i + 2], uu[4 * i + 3]));
+          __stcs(&puv[tl4<32>(t, r, 64 + c0 + ch * 16 + 4 * i)], make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]));
         }
       }
       float mv[16];
@@ -446,8 +448,8 @@ __device__ __forceinline__ void ac3_second16(const float4* uv4, size_t uvo, cons
                                              uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    const float4 u4 = uv4[uvo + (size_t)i * 128];
-    const float4 v4 = uv4[uvo + (size_t)(16 + i) * 128];
+    const float4 u4 = __ldcs(uv4 + uvo + (size_t)i * 128);  // read once: streaming
+    const float4 v4 = __ldcs(uv4 + uvo + (size_t)(16 + i) * 128);
     const float4 g4 = *reinterpret_cast<const float4*>(gmrow + 4 * i);
     const float uu[4] = {u4.x, u4.y, u4.z, u4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
     float wab4[4], wabp4[4];

@@ -887,7 +887,7 @@ __global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const 
             float4* pd = reinterpret_cast<float4*>(a.ds_save);
 #pragma unroll
             for (int i = 0; i < 4; i++)
-              pd[tl4<32>(t, r, cb + ch * 16 + 4 * i)] = make_float4(dsv[4 * i], dsv[4 * i + 1], dsv[4 * i + 2], dsv[4 * i + 3]);
+              __stcs(&pd[tl4<32>(t, r, cb + ch * 16 + 4 * i)], make_float4(dsv[4 * i], dsv[4 * i + 1], dsv[4 * i + 2], dsv[4 * i + 3]));
           }
           tmem_st16(tlane + COL_H + c0 + ch * 16, hi);
           tmem_st16(tlane + COL_H + 64 + c0 + ch * 16, lo);
@@ -957,8 +957,8 @@ __global__ void __launch_bounds__(512, 1) k_line_fwd_tc(const LineArgs a, const 
         float4* puv = reinterpret_cast<float4*>(a.uv_save);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          puv[tl4<32>(t, r, c0 + ch * 16 + 4 * i)] = make_float4(uf[4 * i], uf[4 * i + 1], uf[4 * i + 2], uf[4 * i + 3]);
-          puv[tl4<32>(t, r, 64 + c0 + ch * 16 + 4 * i)] = make_float4(vf[4 * i], vf[4 * i + 1], vf[4 * i + 2], vf[4 * i + 3]);
+          __stcs(&puv[tl4<32>(t, r, c0 + ch * 16 + 4 * i)], make_float4(uf[4 * i], uf[4 * i + 1], uf[4 * i + 2], uf[4 * i + 3]));
+          __stcs(&puv[tl4<32>(t, r, 64 + c0 + ch * 16 + 4 * i)], make_float4(vf[4 * i], vf[4 * i + 1], vf[4 * i + 2], vf[4 * i + 3]));
         }
       }
 #pragma unroll
@@ -1147,7 +1147,7 @@ __global__ void __launch_bounds__(512, 1) k_line_bwd_tc(const LineArgs a, const 
         const float4* ds4 = reinterpret_cast<const float4*>(a.ds);
         float4 dsr[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) dsr[i] = ds4[tl4<32>(t, r, cb + i * 4)];
+        for (int i = 0; i < 8; i++) dsr[i] = __ldcs(ds4 + tl4<32>(t, r, cb + i * 4));  // read once: streaming
         mbar_wait_(&mbar[br], phase);
         tc_fence_after();
 #pragma unroll
