@@ -17,7 +17,7 @@ SYMBOLS = [
     "b2m_create", "b2m_destroy", "b2m_last_error", "b2m_load_weights", "b2m_set_element_refs",
     "b2m_finalize_weights", "b2m_set_scaling", "b2m_comm_unique_id", "b2m_comm_init", "b2m_set_partition", "b2m_set_structure", "b2m_compute",
     "b2m_compute_resident", "b2m_get_sitewise", "b2m_get_counts", "b2m_get_partition_info",
-    "b2m_debug_tensor", "b2m_last_timings", "b2m_release_workspace",
+    "b2m_debug_tensor", "b2m_last_timings", "b2m_release_workspace", "b2m_set_view",
 ]
 
 
@@ -72,6 +72,7 @@ def load_library():
     lib.b2m_debug_tensor.argtypes = [vp, C.c_char_p, P(C.c_float), i64, P(i64), P(i64)]
     lib.b2m_last_timings.argtypes = [vp, P(dbl), i32]
     lib.b2m_release_workspace.argtypes = [vp]
+    lib.b2m_set_view.argtypes = [vp, i32]
     for s in SYMBOLS:
         if s not in ("b2m_last_error", "b2m_get_partition_info"):
             getattr(lib, s).restype = C.c_int
@@ -190,7 +191,17 @@ class Engine:
         self._ck(self.lib.b2m_get_sitewise(self.h, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
-    def counts(self):
+    def set_view(self, part):
+        """single-process group: the partition that counts() / partition_info() describe"""
+        self._ck(self.lib.b2m_set_view(self.h, int(part)))
+
+    def counts(self, partition=None):
+        if partition is not None:
+            self.set_view(partition)
+            try:
+                return self.counts()
+            finally:
+                self.set_view(0)
         out = (C.c_int64 * 10)()
         self._ck(self.lib.b2m_get_counts(self.h, out, 10))
         keys = ["n_own", "n_halo", "n_edges", "n_bond_own", "n_bond_halo", "n_angles", "axis", "rank", "world",

@@ -146,6 +146,7 @@ struct b2m_engine {
   int hpoint = 0;
   DBuf<float> precv[2];            // adjoint rows pushed by my neighbours (backward), double-buffered by point parity
   DBuf<float> ftmp;                // leader: staging of a peer's force array
+  int view = 0;                    // leader: partition addressed by the inspection calls (b2m_set_view)
   // page-locked staging owned by the library: host arrays go through it with a few copy threads (a single-threaded
   // memcpy of 24 MB of positions was the largest host item of an end-to-end step at 1 M atoms)
   void* pin_in = nullptr;   // [N,3] f64 positions followed by [N] i32 species
@@ -1084,6 +1085,9 @@ static void fetch(b2m_engine* e, double* energy, float* forces, float* stress9) 
 
 static std::string g_create_err;
 
+// partition of a single-process group that the inspection calls address (b2m_set_view; the handle itself otherwise)
+static b2m_engine* viewed(b2m_engine* h) { return h->parts.empty() ? h : h->parts[h->view]; }
+
 // every partition of a single-process group holds the replicated weights (chgnet.py:455-549 deep-copies them per GPU)
 template <class F>
 static void each_member(b2m_engine* h, F fn) {
@@ -1370,21 +1374,33 @@ int b2m_get_sitewise(b2m_handle h, float* out) {
   API_END
 }
 
+int b2m_set_view(b2m_handle h, int part) {
+  API_BEGIN
+  const int n = h->parts.empty() ? 1 : (int)h->parts.size();
+  B2M_REQUIRE(part >= 0 && part < n, B2M_ERR_PARTITIONS, "no such partition in this handle");
+  h->view = part;
+  API_END
+}
+
 int b2m_get_counts(b2m_handle h, int64_t* out, int n) {
   API_BEGIN
   B2M_REQUIRE(out && n >= 10, B2M_ERR_INVALID, "need room for 10 counts");
-  Graph& g = h->g;
+  b2m_engine* v = viewed(h);
+  Graph& g = v->g;
   out[0] = g.n_own, out[1] = g.n_halo, out[2] = g.E, out[3] = g.B_own, out[4] = g.B_halo, out[5] = g.A;
-  out[6] = g.axis, out[7] = h->rank, out[8] = h->world, out[9] = h->launches_last;
+  out[6] = g.axis, out[7] = v->rank, out[8] = v->world, out[9] = h->launches_last;
   API_END
 }
 
 int64_t b2m_get_partition_info(b2m_handle h, int which, int64_t* out, int64_t cap) {
   if (!h) return B2M_ERR_INVALID;
   try {
+    b2m_engine* v = viewed(h);
+    cudaSetDevice(v->device);
+    B2M_REQUIRE(v->have_graph && out, B2M_ERR_STATE, "no structure");
+    const int64_t n = v->g.export_info(v->st, which, out, cap);
     cudaSetDevice(h->device);
-    B2M_REQUIRE(h->have_graph && out, B2M_ERR_STATE, "no structure");
-    return h->g.export_info(h->st, which, out, cap);
+    return n;
   } catch (const b2m::Error& ex) {
     h->err = ex.what();
     return ex.code;

@@ -2,10 +2,11 @@
 
 Mirror of DistMLIP/distributed/dist.py (class Distributed).  In the reference this object holds the
 19 host arrays produced by the C extension for *all* partitions and moves halo rows between GPUs
-with cross-device slice assignment (dist.py:323-388).  Here the graph of *this rank's* partition is
-built and kept on the GPU by libb200mlip (b2m_set_structure); halo exchange is NCCL point-to-point
-inside b2m_compute.  The accessors below expose the same counters (dist.py:462-551) and, for tests,
-the partition content in canonical form.
+with cross-device slice assignment (dist.py:323-388).  Here every partition's graph is built and kept on
+its GPU by libb200mlip (b2m_set_structure) and the halo exchange happens inside b2m_compute.  The accessors
+below expose the same counters with the same optional `partition` argument (dist.py:462-551): in a
+single-process group (the reference's setting) any partition can be asked for; under one-process-per-GPU
+each rank sees its own.  For tests, the partition content is available in canonical form.
 """
 from __future__ import annotations
 
@@ -24,6 +25,7 @@ class Distributed:
         c = engine.counts()
         self.counts = c
         self.rank = c["rank"]
+        self._group = bool(getattr(engine, "group", False))
         self.total_num_edges = None  # global count needs a reduction over ranks; see num_atom_edges
         self.forces = None
         self.stress = None
@@ -60,27 +62,51 @@ class Distributed:
         obj.cart = cart_coords
         return obj
 
-    # ---- counters (dist.py:462-551), for this rank's partition ----
+    # ---- counters (dist.py:462-551) ----
+    def _c(self, partition):
+        """counts of `partition` (None: this rank's partition / partition 0 of a group)"""
+        if partition is None or (not self._group and partition == self.rank):
+            return self.counts
+        if not self._group:
+            raise ValueError(f"partition {partition} lives in another process (this rank owns partition {self.rank})")
+        if not 0 <= partition < self.num_partitions:
+            raise ValueError(f"partition {partition} out of range [0, {self.num_partitions})")
+        return self.engine.counts(partition)
+
     def num_atoms(self, partition=None):
-        return self.counts["n_own"] + self.counts["n_halo"]
+        c = self._c(partition)
+        return c["n_own"] + c["n_halo"]
 
     def num_atom_edges(self, partition=None):
-        return self.counts["n_edges"]
+        return self._c(partition)["n_edges"]
 
     def num_bonds(self, partition=None):
         assert self.use_bond_graph, "num_bonds only works when bond graph is enabled"
-        return self.counts["n_bond_own"] + self.counts["n_bond_halo"]
+        c = self._c(partition)
+        return c["n_bond_own"] + c["n_bond_halo"]
 
     def num_bond_edges(self, partition=None):
         assert self.use_bond_graph, "num_bond_edges only works when bond graph is enabled"
-        return self.counts["n_angles"]
+        return self._c(partition)["n_angles"]
 
     def num_atom_border_nodes(self, partition=None):
-        return self.counts["n_halo"]
+        return self._c(partition)["n_halo"]
 
     def num_bond_border_nodes(self, partition=None):
         assert self.use_bond_graph, "num_bond_border_nodes only works when bond graph is enabled"
-        return self.counts["n_bond_halo"]
+        return self._c(partition)["n_bond_halo"]
+
+    def partition_content(self, partition, which):
+        """canonical content (b2m_get_partition_info `which`) of any partition of a single-process group"""
+        if not self._group:
+            if partition != self.rank:
+                raise ValueError("only this rank's partition is visible in one-process-per-GPU mode")
+            return self.engine.partition_info(which)
+        self.engine.set_view(partition)
+        try:
+            return self.engine.partition_info(which)
+        finally:
+            self.engine.set_view(0)
 
     # ---- canonical partition content (tests) ----
     def owned_gids(self):
@@ -109,10 +135,13 @@ class Distributed:
         val = f"""Distributed:
     Total num atoms: {self.total_num_nodes}
     Bond graph exists: {self.use_bond_graph}\n"""
-        val += f"Partition {self.rank} (of {self.num_partitions}):\n"
-        val += f"\t# of atom graph nodes: {self.num_atoms()} ({c['n_halo']} border nodes)\n"
-        val += f"\t# of atom graph edges: {c['n_edges']}"
-        if self.use_bond_graph:
-            val += f"\t# of bond graph nodes: {self.num_bonds()}. ({c['n_bond_halo']} border nodes)\n"
-            val += f"\t# of bond graph edges: {c['n_angles']}"
-        return val + "\n"
+        parts = range(self.num_partitions) if self._group else [self.rank]
+        for p in parts:  # dist.py:704-721 prints every partition; under one process per GPU only this rank's is here
+            c = self._c(p)
+            val += f"Partition {p} (of {self.num_partitions}):\n"
+            val += f"\t# of atom graph nodes: {c['n_own'] + c['n_halo']} ({c['n_halo']} border nodes)\n"
+            val += f"\t# of atom graph edges: {c['n_edges']}\n"
+            if self.use_bond_graph:
+                val += f"\t# of bond graph nodes: {c['n_bond_own'] + c['n_bond_halo']}. ({c['n_bond_halo']} border nodes)\n"
+                val += f"\t# of bond graph edges: {c['n_angles']}\n"
+        return val

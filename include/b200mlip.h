@@ -69,9 +69,9 @@ typedef struct {
  *   ndev  > 1: a single-process group: partition p runs on devices[p] (ordinals may repeat, e.g.
  *              {0, 0} = two partitions on one GPU), one host thread + stream per partition inside
  *              b2m_set_structure / b2m_compute, halo rows exchanged as direct peer-memory stores
- *              ordered by CUDA events (no NCCL).  b2m_get_counts / b2m_get_partition_info /
- *              b2m_debug_tensor then describe partition 0; energies, forces, stress and the
- *              site-wise readout are those of the whole structure. */
+ *              ordered by CUDA events (no NCCL).  b2m_get_counts / b2m_get_partition_info describe
+ *              the partition chosen with b2m_set_view (default 0), b2m_debug_tensor partition 0;
+ *              energies, forces, stress and the site-wise readout are those of the whole structure. */
 int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_handle* out);
 int b2m_destroy(b2m_handle h);
 const char* b2m_last_error(b2m_handle h);
@@ -107,6 +107,11 @@ int b2m_compute_resident(b2m_handle h, int want_forces, int want_stress, int rep
 
 /* site-wise readout (magmom) for all atoms, [natoms] */
 int b2m_get_sitewise(b2m_handle h, float* out);
+
+/* Single-process groups: which partition b2m_get_counts / b2m_get_partition_info describe (default 0).  The reference's
+ * Distributed keeps every partition's arrays on the host (dist.py:39-99) and its counters take a `partition` argument
+ * (dist.py:462-551); this is the equivalent view. */
+int b2m_set_view(b2m_handle h, int part);
 
 /* counts: [0]=n_own [1]=n_halo [2]=n_edges [3]=n_bond_own [4]=n_bond_halo [5]=n_angles
  *         [6]=partition axis [7]=rank [8]=world [9]=kernel launches in last compute */

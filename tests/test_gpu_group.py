@@ -90,3 +90,44 @@ def test_group_errors_come_back_from_the_partition_threads():
     E, F, S, _ = pot(si_diamond(4, nz=8, seed=1))  # the group stays usable
     assert np.isfinite(F.numpy()).all()
     dm._engine.close()
+
+
+def test_group_partition_views_agree():
+    """the reference keeps every partition's arrays on the host and its counters take a `partition` argument
+    (dist.py:39-99, 462-551); in a single-process group the same questions are answered per partition (b2m_set_view):
+    owned atoms partition the structure, what partition q lists "to p" is exactly p's halo section from q, in order."""
+    atoms = si_diamond(4, nz=12, seed=7)
+    dm, pot = group_potential([0, 0, 0])
+    pot(atoms)
+    d = pot.last_dist_info
+    P = 3
+    own = [d.partition_content(p, 0) for p in range(P)]
+    assert sorted(np.concatenate(own).tolist()) == list(range(len(atoms)))
+    assert sum(d.num_atoms(p) - d.num_atom_border_nodes(p) for p in range(P)) == len(atoms)
+    for p in range(P):
+        halo, howner = d.partition_content(p, 1), d.partition_content(p, 2)
+        assert d.num_atom_border_nodes(p) == len(halo) and d.num_bond_border_nodes(p) > 0
+        for q in range(P):
+            if q == p:
+                continue
+            tl = d.partition_content(q, 6)
+            assert np.array_equal(tl[tl[:, 0] == p, 1], halo[howner == q])
+    text = repr(d)
+    assert text.count("Partition ") == 3 and "border nodes" in text
+    with pytest.raises(ValueError):
+        d.num_atoms(5)
+    dm._engine.close()
+
+
+def test_group_triclinic_cell():
+    """sheared cell, two partitions: slab walls in wrapped fractional coordinate of a non-orthogonal lattice"""
+    a = si_diamond(4, nz=9, seed=15)
+    lat = a.get_cell()
+    lat[2, 0], lat[1, 0] = 3.0, 1.5
+    atoms = SimpleAtoms(a.get_chemical_symbols(), a.get_scaled_positions() @ lat, lat)
+    dm, pot = group_potential([0, 0])
+    E, F, S, _ = pot(atoms)
+    Eo, Fo, So, _ = potential_ref(make_model(), atoms)
+    assert abs(E.item() - Eo.item()) / len(atoms) < TOL_E
+    assert (F - Fo).abs().max().item() < TOL_F and (S - So).abs().max().item() < TOL_S
+    dm._engine.close()
