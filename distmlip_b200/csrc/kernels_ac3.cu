@@ -144,14 +144,14 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_fwd_v3(const AtomConvArgs a
   };
   auto load_be = [&](int64_t t, float4 (&b)[3]) {
     const float4* bp = reinterpret_cast<const float4*>(a.be);
-    b[0] = bp[tl4<3>(t, r, 0)], b[1] = bp[tl4<3>(t, r, 4)], b[2] = bp[tl4<3>(t, r, 8)];
+    b[0] = __ldcs(bp + tl4<3>(t, r, 0)), b[1] = __ldcs(bp + tl4<3>(t, r, 4)), b[2] = __ldcs(bp + tl4<3>(t, r, 8));  // streamed once per launch
   };
   float4 benext[3];
   if (t_first < ntiles) {
     if (gt < 128) {
       int src = 0, dst = -1, bond = -1;
       const int64_t e = t_first * 128 + gt;
-      if (e < a.E) src = a.e_src[e], dst = a.e_dst[e], bond = a.e_bond[e];
+      if (e < a.E) src = __ldcs(a.e_src + e), dst = __ldcs(a.e_dst + e), bond = __ldcs(a.e_bond + e);
       idx[gt] = src, idx[128 + gt] = dst, idx[256 + gt] = bond;
     }
     load_be(t_first, benext);
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_fwd_v3(const AtomConvArgs a
     int nsrc = 0, ndst = -1, nbond = -1;
     if (have_next && gt < 128) {
       const int64_t e = tn * 128 + gt;
-      if (e < a.E) nsrc = a.e_src[e], ndst = a.e_dst[e], nbond = a.e_bond[e];
+      if (e < a.E) nsrc = __ldcs(a.e_src + e), ndst = __ldcs(a.e_dst + e), nbond = __ldcs(a.e_bond + e);
     }
     float bek[9];
     bek[0] = benext[0].x, bek[1] = benext[0].y, bek[2] = benext[0].z, bek[3] = benext[0].w, bek[4] = benext[1].x;
@@ -523,15 +523,15 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_bwd_v3(const AtomConvArgs a
   auto load_be = [&](int64_t t, float4 (&b)[3], float4 (&d)[3]) {
     const float4* bp = reinterpret_cast<const float4*>(a.be);
     const float4* dp = reinterpret_cast<const float4*>(a.dbe);
-    b[0] = bp[tl4<3>(t, r, 0)], b[1] = bp[tl4<3>(t, r, 4)], b[2] = bp[tl4<3>(t, r, 8)];
-    d[0] = dp[tl4<3>(t, r, 0)], d[1] = dp[tl4<3>(t, r, 4)], d[2] = dp[tl4<3>(t, r, 8)];
+    b[0] = __ldcs(bp + tl4<3>(t, r, 0)), b[1] = __ldcs(bp + tl4<3>(t, r, 4)), b[2] = __ldcs(bp + tl4<3>(t, r, 8));  // streamed once per launch
+    d[0] = __ldcs(dp + tl4<3>(t, r, 0)), d[1] = __ldcs(dp + tl4<3>(t, r, 4)), d[2] = __ldcs(dp + tl4<3>(t, r, 8));
   };
   float4 benext[3], dbenext[3];
   if (t_first < ntiles) {
     if (gt < 128) {
       int src = 0, dst = -1, bond = -1;
       const int64_t e = t_first * 128 + gt;
-      if (e < a.E) src = a.e_src[e], dst = a.e_dst[e], bond = a.e_bond[e];
+      if (e < a.E) src = __ldcs(a.e_src + e), dst = __ldcs(a.e_dst + e), bond = __ldcs(a.e_bond + e);
       idx[gt] = src, idx[128 + gt] = dst, idx[256 + gt] = bond;
     }
     load_be(t_first, benext, dbenext);
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(512, 1) k_atomconv_bwd_v3(const AtomConvArgs a
     int nsrc = 0, ndst = -1, nbond = -1;
     if (have_next && gt < 128) {
       const int64_t e = tn * 128 + gt;
-      if (e < a.E) nsrc = a.e_src[e], ndst = a.e_dst[e], nbond = a.e_bond[e];
+      if (e < a.E) nsrc = __ldcs(a.e_src + e), ndst = __ldcs(a.e_dst + e), nbond = __ldcs(a.e_bond + e);
     }
     if (have_next) {  // streamed operands of my next tile: DRAM -> L2 while this tile computes
       l2_prefetch(a.uv + tn * (128 * 128), 128 * 128 * 4, gt, 256);
