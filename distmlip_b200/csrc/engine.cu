@@ -1,6 +1,7 @@
 // engine.cu -- host orchestration behind the C-ABI (include/b200mlip.h):
-// weight composition, GPU-resident workspace, forward + hand-derived backward schedule, NCCL halo
-// exchange between slab neighbours, and the extern "C" entry points.
+// weight composition, GPU-resident workspace, forward + hand-derived backward schedule, halo exchange
+// between slab neighbours (NCCL point-to-point between processes, peer-memory stores inside a
+// single-process group), and the extern "C" entry points.
 //
 // Schedule mirrors (and is verified stage-by-stage against) oracle/manual_ref.py; the reference
 // control flow it replaces is DistMLIP/implementations/matgl/models/chgnet.py:208-453 (forward)

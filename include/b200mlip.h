@@ -17,10 +17,12 @@
  *        CHGNet_Dist.dist_forward (chgnet.py:208-453) + Potential_Dist.forward's scaling,
  *        torch.autograd.backward, F = -grad, sigma = strain.grad / V * 160.21766208
  *        (DistMLIP/implementations/matgl/pes.py:50-146).
- *   b2m_comm_unique_id / b2m_comm_init
+ *   b2m_create with ndev > 1, or b2m_comm_unique_id / b2m_comm_init
  *        the reference has no communicator: Distributed.transfer_nodes does cross-device
- *        slice copies from one thread (dist.py:323-358).  Here: one process per GPU, NCCL
- *        point-to-point halo exchange between slab neighbours.
+ *        slice copies from one thread (dist.py:323-358).  Here either one process drives every
+ *        GPU (ndev > 1: peer-memory halo stores ordered by CUDA events, one host thread per
+ *        partition) or one process per GPU with NCCL point-to-point halo exchange between slab
+ *        neighbours.
  *   b2m_get_partition_info
  *        the 19-tuple returned by get_subgraphs_fast (subgraph_creation_fast.c:403-422), in
  *        canonical (set) form, for parity tests.
