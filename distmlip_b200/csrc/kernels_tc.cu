@@ -1,6 +1,8 @@
-// kernels_tc.cu -- tcgen05 / TMEM versions of the fused tile kernels (sm_100a).
+// kernels_tc.cu -- tcgen05 / TMEM versions of the fused tile kernels (sm_100a): the line-graph kernels (bond conv, angle
+// update: default path), the row GEMMs (default path) and the FIRST generation of the atom-conv kernels, which the third
+// generation in kernels_ac3.cu replaced as the default in round 2 (kept selectable with B2M_ATOMCONV=1 for A/B checks).
 //
-// Design (atom conv forward, the edge-gather kernel of the headline metric):
+// Design of the first-generation atom conv forward:
 //   * persistent CTAs, 256 threads, 2 CTAs per SM, 256 TMEM columns each: [H operand 128 | D accum 128]
 //   * thread <-> row mapping fixed by TMEM: warp w owns lanes 32*(w%4)..+31, half = w/4 picks 32 of 64 columns
 //   * A operands live in TMEM (tcgen05.st from registers, hi/lo tf32 split) -- no shared-memory A tiles
