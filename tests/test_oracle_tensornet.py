@@ -1,0 +1,57 @@
+"""CPU: the stage-by-stage TensorNet mirror (oracle/tensornet_manual.py, the layout and reverse pass the CUDA kernels
+follow) against autograd through the module restatement (oracle/tensornet_ref.py)."""
+import numpy as np
+import pytest
+import torch
+
+from distmlip_b200.structures import SimpleAtoms, rough_cell, si_diamond
+from oracle import graph_ref as G
+from oracle import tensornet_manual as TM
+from oracle.manual_ref import forces_from_gvec
+from oracle.tensornet_ref import TensorNetRef, potential_ref
+
+
+def make_tn(seed=0, scale=1.0, **kw):
+    torch.manual_seed(seed)
+    m = TensorNetRef(**kw)
+    if scale != 1.0:
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if "weight" in n and p.ndim == 2 and ".emb." not in n:
+                    p.mul_(scale)
+    return m
+
+
+def tn_graph(atoms, rc=5.0):
+    cart, lat = atoms.get_positions(), np.array(atoms.get_cell())
+    i1, i2, off, _d2, _b = G.neighbor_list(cart, lat, atoms.get_pbc().astype(np.int64), rc, 0.0)
+    return dict(i1=i1, i2=i2, off=off, vec=cart[i2] + off @ lat - cart[i1])
+
+
+@pytest.mark.parametrize("group", ["O(3)", "SO(3)"])
+def test_manual_mirror_equals_autograd(group):
+    a0 = si_diamond(2, sigma=0.15, seed=1)
+    atoms = SimpleAtoms(["Si" if i % 3 else "O" for i in range(len(a0))], a0.get_positions(), a0.get_cell())
+    m = make_tn(seed=3, scale=1.5, equivariance_invariance_group=group)
+    og = tn_graph(atoms)
+    E, F, S = potential_ref(m, atoms, graph=(og["i1"], og["i2"], og["off"]), dtype=torch.float64, data_std=1.3)
+    types = np.array([m.element_types.index(s) for s in atoms.get_chemical_symbols()])
+    out = TM.run(m, types, og["vec"], og["i1"], og["i2"], data_std=1.3)
+    assert abs(1.3 * float(out["energy"]) - float(E)) < 1e-10 * max(1.0, abs(float(E)))
+    Fm, Sm = forces_from_gvec(out["gvec"], og["vec"], og["i1"], og["i2"], len(atoms), atoms.get_volume())
+    assert float((Fm - F).abs().max()) < 1e-10 * max(1.0, float(F.abs().max()))
+    assert float((Sm - S).abs().max()) < 1e-10 * max(1.0, float(S.abs().max()))
+
+
+def test_oracle_symmetries():
+    """rotation invariance of the energy / equivariance of the forces, and translation invariance."""
+    atoms = rough_cell(40, seed=2)
+    m = make_tn(seed=1, scale=1.5)
+    E, F, _ = potential_ref(m, atoms, dtype=torch.float64)
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    cell = np.array(atoms.get_cell()) @ R.T
+    b = SimpleAtoms(atoms.get_chemical_symbols(), atoms.get_positions() @ R.T + np.array([0.37, 0.11, -0.2]) @ cell, cell)
+    E2, F2, _ = potential_ref(m, b, dtype=torch.float64)
+    assert abs(float(E2 - E)) < 1e-9
+    assert np.abs(F2.numpy() - F.numpy() @ R.T).max() < 1e-9
