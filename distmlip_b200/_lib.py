@@ -17,7 +17,7 @@ SYMBOLS = [
     "b2m_create", "b2m_destroy", "b2m_last_error", "b2m_load_weights", "b2m_set_element_refs",
     "b2m_finalize_weights", "b2m_set_scaling", "b2m_comm_unique_id", "b2m_comm_init", "b2m_set_partition", "b2m_set_structure", "b2m_compute",
     "b2m_compute_resident", "b2m_get_sitewise", "b2m_get_counts", "b2m_get_partition_info",
-    "b2m_debug_tensor", "b2m_last_timings", "b2m_release_workspace", "b2m_set_view",
+    "b2m_debug_tensor", "b2m_last_timings", "b2m_release_workspace", "b2m_set_view", "b2m_create_tensornet",
 ]
 
 
@@ -27,6 +27,14 @@ class ModelDesc(C.Structure):
         ("n_blocks", C.c_int32), ("cutoff_exponent", C.c_int32),
         ("cutoff", C.c_double), ("three_body_cutoff", C.c_double),
         ("data_mean", C.c_double), ("data_std", C.c_double),
+    ]
+
+
+class TensorNetDesc(C.Structure):
+    _fields_ = [
+        ("n_elem", C.c_int32), ("units", C.c_int32), ("num_rbf", C.c_int32), ("n_blocks", C.c_int32),
+        ("so3", C.c_int32), ("reserved", C.c_int32),
+        ("cutoff", C.c_double), ("rbf_width", C.c_double), ("data_mean", C.c_double), ("data_std", C.c_double),
     ]
 
 
@@ -52,6 +60,7 @@ def load_library():
     vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
     P = C.POINTER
     lib.b2m_create.argtypes = [P(ModelDesc), P(C.c_int), i32, P(vp)]
+    lib.b2m_create_tensornet.argtypes = [P(TensorNetDesc), P(C.c_int), i32, P(vp)]
     lib.b2m_destroy.argtypes = [vp]
     lib.b2m_last_error.argtypes = [vp]
     lib.b2m_last_error.restype = C.c_char_p
@@ -93,15 +102,24 @@ class Engine:
     """Thin RAII wrapper over a b2m_handle.  `device`: one CUDA ordinal (one partition, or one rank of a multi-process
     job) or a list of ordinals = a single-process group with one partition per entry (ordinals may repeat)."""
 
-    def __init__(self, *, n_elem, dim, max_n, max_f, n_blocks, cutoff, three_body_cutoff, cutoff_exponent,
-                 data_mean=0.0, data_std=1.0, device=0):
+    def __init__(self, *, n_elem, dim=64, max_n=9, max_f=4, n_blocks, cutoff, three_body_cutoff=0.0, cutoff_exponent=0,
+                 data_mean=0.0, data_std=1.0, device=0, tensornet=None):
+        """`tensornet`: None for CHGNet, else dict(units=, num_rbf=, so3=, rbf_width=) for a TensorNet handle
+        (b2m_create_tensornet); everything after construction is the same."""
         self.lib = load_library()
-        self.desc = ModelDesc(n_elem, dim, max_n, max_f, n_blocks, cutoff_exponent, cutoff, three_body_cutoff,
-                              data_mean, data_std)
         self.h = C.c_void_p()
         devs = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
         dev = (C.c_int * len(devs))(*devs)
-        rc = self.lib.b2m_create(C.byref(self.desc), dev, len(devs), C.byref(self.h))
+        self.kind = "chgnet" if tensornet is None else "tensornet"
+        if tensornet is None:
+            self.desc = ModelDesc(n_elem, dim, max_n, max_f, n_blocks, cutoff_exponent, cutoff, three_body_cutoff,
+                                  data_mean, data_std)
+            rc = self.lib.b2m_create(C.byref(self.desc), dev, len(devs), C.byref(self.h))
+        else:
+            self.desc = TensorNetDesc(n_elem, int(tensornet["units"]), int(tensornet["num_rbf"]), n_blocks,
+                                      int(bool(tensornet.get("so3", False))), 0, cutoff, float(tensornet["rbf_width"]),
+                                      data_mean, data_std)
+            rc = self.lib.b2m_create_tensornet(C.byref(self.desc), dev, len(devs), C.byref(self.h))
         if rc != 0:
             raise B2MError(rc, (self.lib.b2m_last_error(None) or b"").decode())
         self.natoms = 0

@@ -20,8 +20,11 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
 #include "graph.cuh"
 #include "kernels.cuh"
+#include "tn_state.cuh"
 
 namespace b2m {
 
@@ -113,6 +116,8 @@ struct GroupSync {
 
 struct b2m_engine {
   b2m_model_desc desc;
+  int kind = 0;                   // 0: CHGNet (b2m_create), 1: TensorNet (b2m_create_tensornet)
+  b2m::TnState* tn = nullptr;     // TensorNet weights and workspace (kind 1)
   int device = 0;
   cudaStream_t st = nullptr;
   cudaStream_t cst = nullptr;            // halo traffic of the forward pass (overlaps the projections that do not need it)
@@ -558,7 +563,11 @@ static void alloc_workspace(b2m_engine* e) {
 // group, direct peer-memory traffic: the sender's pack kernel stores its boundary rows straight into the receiver's halo
 // rows (forward) or copies its halo adjoints into the owner's receive buffer (backward); a CUDA event per exchange point
 // orders the receiver's stream behind the sender's.
-static float* halo_buffer(b2m_engine* e, bool bonds, int l) { return bonds ? e->h[l].p : e->x[l].p; }
+// kind 0: atom rows x[l] | 1: bond rows h[l] | 2: TensorNet atom tensors X[l] (10 x 64 floats per atom)
+static float* halo_buffer(b2m_engine* e, int kind, int l) {
+  return kind == 1 ? e->h[l].p : (kind == 2 ? e->tn->X[l].p : e->x[l].p);
+}
+static int halo_width(int kind) { return kind == 2 ? 10 * D : D; }
 
 static cudaEvent_t next_halo_event(b2m_engine* e) {
   // the events are created in b2m_create: a neighbour's thread reads hev[k] concurrently, so the vector never grows here
@@ -571,10 +580,12 @@ static cudaEvent_t next_halo_event(b2m_engine* e) {
 // that do not read the halo rows (the reference issues its copies on the compute stream, dist.py:344-356):
 //   halo_forward_begin: [compute: producer done] -> [comm stream: pack, send / receive or peer stores]
 //   halo_forward_end  : compute stream waits for the exchange (and, in a group, for the neighbours' stores)
-static void halo_forward_begin(b2m_engine* e, bool bonds, int l) {
+static void halo_forward_begin(b2m_engine* e, int kind, int l) {
   if (e->world <= 1 || e->debug_no_halo) return;
   Graph& g = e->g;
-  float* buf = halo_buffer(e, bonds, l);
+  const bool bonds = kind == 1;
+  const size_t W = (size_t)halo_width(kind);
+  float* buf = halo_buffer(e, kind, l);
   const int* nto = bonds ? g.nb_to : g.n_to;
   const int* toff = bonds ? g.bto_off : g.to_off;
   const int* nfrom = bonds ? g.nb_from : g.n_from;
@@ -593,20 +604,21 @@ static void halo_forward_begin(b2m_engine* e, bool bonds, int l) {
       B2M_REQUIRE(pn == nto[q], B2M_ERR_STATE, "halo sections of two partitions disagree");
       const size_t pbase = bonds ? (size_t)pg.B_own : (size_t)pg.n_own;
       const size_t pfoff = bonds ? (size_t)pg.bfrom_off[e->rank] : (size_t)pg.from_off[e->rank];
-      launch_gather_rows(e->cst, nto[q], D, list + toff[q], buf, halo_buffer(pe, bonds, l) + (pbase + pfoff) * D);
+      launch_gather_rows(e->cst, nto[q], (int)W, list + toff[q], buf, halo_buffer(pe, kind, l) + (pbase + pfoff) * W);
     }
     B2M_CK(cudaEventRecord(next_halo_event(e), e->cst));
     return;
   }
   for (int q = 0; q < e->world; q++)
-    if (nto[q] > 0) launch_gather_rows(e->cst, nto[q], D, list + toff[q], buf, e->sendbuf.p + (size_t)toff[q] * D);
+    if (nto[q] > 0)
+      launch_gather_rows(e->cst, nto[q], (int)W, list + toff[q], buf, e->sendbuf.p + (size_t)toff[q] * W);
   NCCL_CK(g_nccl.GroupStart());
   for (int q = 0; q < e->world; q++) {
     if (q == e->rank) continue;
     if (nto[q] > 0)
-      NCCL_CK(g_nccl.Send(e->sendbuf.p + (size_t)toff[q] * D, (size_t)nto[q] * D, ncclFloat32, q, e->comm, e->cst));
+      NCCL_CK(g_nccl.Send(e->sendbuf.p + (size_t)toff[q] * W, (size_t)nto[q] * W, ncclFloat32, q, e->comm, e->cst));
     if (nfrom[q] > 0)
-      NCCL_CK(g_nccl.Recv(buf + (base + foff[q]) * D, (size_t)nfrom[q] * D, ncclFloat32, q, e->comm, e->cst));
+      NCCL_CK(g_nccl.Recv(buf + (base + foff[q]) * W, (size_t)nfrom[q] * W, ncclFloat32, q, e->comm, e->cst));
   }
   NCCL_CK(g_nccl.GroupEnd());
   B2M_CK(cudaEventRecord(e->ev_halo, e->cst));
@@ -624,9 +636,10 @@ static void halo_forward_end(b2m_engine* e) {
   B2M_CK(cudaStreamWaitEvent(e->st, e->ev_halo, 0));
 }
 // backward: my halo rows of the adjoint -> owners (accumulate), then zero the halo rows
-static void halo_backward(b2m_engine* e, float* gbuf, bool bonds) {
+static void halo_backward(b2m_engine* e, float* gbuf, bool bonds, int width = D) {
   if (e->world <= 1 || e->debug_no_halo) return;
   Graph& g = e->g;
+  const size_t W = (size_t)width;
   const int* nto = bonds ? g.nb_to : g.n_to;
   const int* toff = bonds ? g.bto_off : g.to_off;
   const int* nfrom = bonds ? g.nb_from : g.n_from;
@@ -642,10 +655,10 @@ static void halo_backward(b2m_engine* e, float* gbuf, bool bonds) {
       b2m_engine* pe = L->parts[q];
       const size_t ptoff = bonds ? (size_t)pe->g.bto_off[e->rank] : (size_t)pe->g.to_off[e->rank];
       // the owner's receive buffer of this parity was consumed two exchange points ago (group mode)
-      B2M_CK(cudaMemcpyAsync(pe->precv[k & 1].p + ptoff * D, gbuf + (base + foff[q]) * D, (size_t)nfrom[q] * D * sizeof(float),
+      B2M_CK(cudaMemcpyAsync(pe->precv[k & 1].p + ptoff * W, gbuf + (base + foff[q]) * W, (size_t)nfrom[q] * W * sizeof(float),
                              cudaMemcpyDefault, e->st));
     }
-    launch_zero_rows(e->st, gbuf + base * D, nhalo * D);
+    launch_zero_rows(e->st, gbuf + base * W, nhalo * W);
     cudaEvent_t ev = next_halo_event(e);
     B2M_CK(cudaEventRecord(ev, e->st));
     e->hpoint++;
@@ -654,23 +667,25 @@ static void halo_backward(b2m_engine* e, float* gbuf, bool bonds) {
       if (q != e->rank) B2M_CK(cudaStreamWaitEvent(e->st, L->parts[q]->hev[k], 0));
     for (int q = 0; q < e->world; q++)
       if (q != e->rank && nto[q] > 0)
-        launch_scatter_add_rows(e->st, nto[q], D, list + toff[q], e->precv[k & 1].p + (size_t)toff[q] * D, gbuf);
+        launch_scatter_add_rows(e->st, nto[q], (int)W, list + toff[q], e->precv[k & 1].p + (size_t)toff[q] * W, gbuf);
     return;
   }
   NCCL_CK(g_nccl.GroupStart());
   for (int q = 0; q < e->world; q++) {
     if (q == e->rank) continue;
     if (nfrom[q] > 0)
-      NCCL_CK(g_nccl.Send(gbuf + (base + foff[q]) * D, (size_t)nfrom[q] * D, ncclFloat32, q, e->comm, e->st));
+      NCCL_CK(g_nccl.Send(gbuf + (base + foff[q]) * W, (size_t)nfrom[q] * W, ncclFloat32, q, e->comm, e->st));
     if (nto[q] > 0)
-      NCCL_CK(g_nccl.Recv(e->recvbuf.p + (size_t)toff[q] * D, (size_t)nto[q] * D, ncclFloat32, q, e->comm, e->st));
+      NCCL_CK(g_nccl.Recv(e->recvbuf.p + (size_t)toff[q] * W, (size_t)nto[q] * W, ncclFloat32, q, e->comm, e->st));
   }
   NCCL_CK(g_nccl.GroupEnd());
   for (int q = 0; q < e->world; q++)
     if (nto[q] > 0)
-      launch_scatter_add_rows(e->st, nto[q], D, list + toff[q], e->recvbuf.p + (size_t)toff[q] * D, gbuf);
-  launch_zero_rows(e->st, gbuf + base * D, nhalo * D);
+      launch_scatter_add_rows(e->st, nto[q], (int)W, list + toff[q], e->recvbuf.p + (size_t)toff[q] * W, gbuf);
+  launch_zero_rows(e->st, gbuf + base * W, nhalo * W);
 }
+
+#include "engine_tn.inl"
 
 static AtomConvArgs atom_args(b2m_engine* e, int l) {
   Graph& g = e->g;
@@ -927,9 +942,11 @@ static void run(b2m_engine* e, bool grads) {
   const long long l0 = g_launch_count;
   B2M_CK(cudaEventRecord(e->ev[0], e->st));
   e->want_grads = grads;
-  forward(e);
+  if (e->kind == 1) tn_forward(e); else forward(e);
   B2M_CK(cudaEventRecord(e->ev[1], e->st));
-  if (grads) backward(e);
+  if (grads) {
+    if (e->kind == 1) tn_backward(e); else backward(e);
+  }
   if (e->world > 1 && e->leader == nullptr && !e->debug_no_halo) {
     NCCL_CK(g_nccl.AllReduce(e->scal.p, e->scal.p, 10, ncclFloat64, ncclSum, e->comm, e->st));
     if (grads)
@@ -1135,22 +1152,42 @@ static b2m_engine* create_one(const b2m_model_desc* desc, int device, int count)
   return e;
 }
 
-int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_handle* out) {
+static int create_any(const b2m_model_desc* desc, const b2m_tensornet_desc* tdesc, const int* devices, int ndev,
+                      b2m_handle* out) {
   if (!desc || !devices || !out) return B2M_ERR_INVALID;
   std::vector<b2m_engine*> made;
   try {
     B2M_REQUIRE(ndev >= 1 && ndev <= MAXP, B2M_ERR_PARTITIONS, "ndev must be in [1,16]");
-    B2M_REQUIRE(desc->dim == D && desc->max_n == NR && desc->max_f == 4, B2M_ERR_INVALID,
-                "engine supports dim=64, max_n=9, max_f=4");
-    B2M_REQUIRE(desc->n_blocks >= 2 && desc->n_blocks <= 16, B2M_ERR_INVALID, "n_blocks must be in [2,16]");
-    B2M_REQUIRE(desc->cutoff > 0 && desc->three_body_cutoff > 0 && desc->three_body_cutoff <= desc->cutoff,
-                B2M_ERR_INVALID, "bond_r cannot be greater than regular cutoff");
+    if (tdesc) {
+      B2M_REQUIRE(tdesc->units == D, B2M_ERR_INVALID, "TensorNet engine supports units = 64");
+      B2M_REQUIRE(tdesc->num_rbf >= 1 && tdesc->num_rbf <= 64, B2M_ERR_INVALID, "num_rbf must be in [1,64]");
+      B2M_REQUIRE(tdesc->n_blocks >= 1 && tdesc->n_blocks <= 16, B2M_ERR_INVALID, "nblocks must be in [1,16]");
+      B2M_REQUIRE(tdesc->cutoff > 0 && tdesc->rbf_width > 0, B2M_ERR_INVALID, "cutoff and rbf width must be positive");
+    } else {
+      B2M_REQUIRE(desc->dim == D && desc->max_n == NR && desc->max_f == 4, B2M_ERR_INVALID,
+                  "engine supports dim=64, max_n=9, max_f=4");
+      B2M_REQUIRE(desc->n_blocks >= 2 && desc->n_blocks <= 16, B2M_ERR_INVALID, "n_blocks must be in [2,16]");
+      B2M_REQUIRE(desc->cutoff > 0 && desc->three_body_cutoff > 0 && desc->three_body_cutoff <= desc->cutoff,
+                  B2M_ERR_INVALID, "bond_r cannot be greater than regular cutoff");
+    }
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count <= 0)
       throw Error(B2M_ERR_CUDA, std::string("no CUDA device available (libb200mlip has no CPU fallback): ") +
                                     cudaGetErrorString(ce));
-    for (int p = 0; p < ndev; p++) made.push_back(create_one(desc, devices[p], count));
+    for (int p = 0; p < ndev; p++) {
+      made.push_back(create_one(desc, devices[p], count));
+      if (tdesc) {
+        b2m_engine* m = made.back();
+        m->kind = 1;
+        m->tn = new TnState();
+        m->tn->units = tdesc->units, m->tn->num_rbf = tdesc->num_rbf, m->tn->nblocks = tdesc->n_blocks;
+        m->tn->so3 = tdesc->so3 ? 1 : 0;
+        m->tn->rp.nr = tdesc->num_rbf, m->tn->rp.nrp = 64;
+        m->tn->rp.width = (float)tdesc->rbf_width, m->tn->rp.rc = (float)tdesc->cutoff;
+        for (float& v : m->tn->rp.mu) v = 0.f;
+      }
+    }
     b2m_engine* e = made[0];
     if (ndev > 1) {
       // single-process group: partition p lives on devices[p] (ordinals may repeat: several partitions on one GPU);
@@ -1175,15 +1212,34 @@ int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_han
     }
     *out = e;
   } catch (const b2m::Error& ex) {
-    for (auto* m : made) delete m;
+    for (auto* m : made) {
+      delete m->tn;
+      delete m;
+    }
     g_create_err = ex.what();
     return ex.code;
   }
   return B2M_OK;
 }
 
+int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_handle* out) {
+  return create_any(desc, nullptr, devices, ndev, out);
+}
+
+int b2m_create_tensornet(const b2m_tensornet_desc* tdesc, const int* devices, int ndev, b2m_handle* out) {
+  if (!tdesc) return B2M_ERR_INVALID;
+  // the shared part of the engine (graph build, scaling, transport) reads the CHGNet-shaped description: no bond graph
+  // (use_bond_graph False, three_body_cutoff 0: pes.py:79-80)
+  b2m_model_desc d;
+  memset(&d, 0, sizeof d);
+  d.n_elem = tdesc->n_elem, d.dim = D, d.max_n = NR, d.max_f = 4, d.n_blocks = tdesc->n_blocks, d.cutoff_exponent = 0;
+  d.cutoff = tdesc->cutoff, d.three_body_cutoff = 0.0, d.data_mean = tdesc->data_mean, d.data_std = tdesc->data_std;
+  return create_any(&d, tdesc, devices, ndev, out);
+}
+
 static void destroy_one(b2m_engine* h) {
   cudaSetDevice(h->device);
+  delete h->tn;  // frees its device buffers
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (auto& p : h->gather_ev) {
     cudaEventDestroy(p.first);
@@ -1251,7 +1307,9 @@ int b2m_set_scaling(b2m_handle h, double data_mean, double data_std) {
 
 int b2m_finalize_weights(b2m_handle h) {
   API_BEGIN
-  each_member(h, [&](b2m_engine* e) { finalize_weights(e); });
+  each_member(h, [&](b2m_engine* e) {
+    if (e->kind == 1) tn_finalize_weights(e); else finalize_weights(e);
+  });
   API_END
 }
 
@@ -1312,7 +1370,7 @@ static void set_structure_one(b2m_engine* h, int64_t natoms, const double* cart,
   B2M_CK(cudaEventRecord(h->ev[3], h->st));
   h->g.build(h->st, natoms, cart, lattice9, species, pbc3, h->desc.cutoff, h->desc.three_body_cutoff, tol, h->rank,
              h->world);
-  alloc_workspace(h);
+  if (h->kind == 1) tn_alloc_workspace(h); else alloc_workspace(h);
   B2M_CK(cudaEventRecord(h->ev[4], h->st));
   B2M_CK(cudaStreamSynchronize(h->st));
   float ms;
@@ -1353,6 +1411,7 @@ int b2m_compute_resident(b2m_handle h, int want_forces, int want_stress, int rep
 int b2m_get_sitewise(b2m_handle h, float* out) {
   API_BEGIN
   B2M_REQUIRE(h->have_graph && out, B2M_ERR_STATE, "no structure");
+  B2M_REQUIRE(h->kind == 0, B2M_ERR_INVALID, "the site-wise readout belongs to CHGNet (TensorNet has none)");
   std::vector<float> full(h->g.N, 0.f);
   auto collect = [&](b2m_engine* e) {  // owned rows of one partition -> global order
     Graph& g = e->g;
@@ -1416,7 +1475,9 @@ int b2m_debug_tensor(b2m_handle h, const char* name, float* out, int64_t cap, in
   const float* src = nullptr;
   int64_t r = 0, c = D;
   auto idx = [&](const std::string& pre) { return atoi(n.c_str() + pre.size()); };
-  if (n[0] == 'x' && isdigit(n[1])) {
+  if (h->kind == 1) {
+    B2M_REQUIRE(tn_debug_lookup(h, n, src, r, c), B2M_ERR_INVALID, "unknown debug tensor: " + n);
+  } else if (n[0] == 'x' && isdigit(n[1])) {
     int l = idx("x");
     B2M_REQUIRE(l >= 0 && l < (int)h->x.size(), B2M_ERR_INVALID, "bad layer");
     src = h->x[l].p, r = l == (int)h->x.size() - 1 ? g.n_own : g.n_loc;
@@ -1480,6 +1541,7 @@ int b2m_release_workspace(b2m_handle h) {
                     &e->gagg, &e->gupd, &e->gaggB, &e->gd, &e->gdb, &e->gbvec, &e->gy1, &e->gy2, &e->forces,
                     &e->sendbuf, &e->recvbuf, &e->site_full, &e->precv[0], &e->precv[1], &e->ftmp})
       drop(*b);
+    tn_release(e);
     e->g.~Graph();  // the resident graph goes too
     new (&e->g) Graph();
   });

@@ -178,3 +178,73 @@ struct LineTcW {
 void launch_line_fwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms);
 void launch_line_bwd_tc(cudaStream_t st, const LineArgs& a, const LineTcW& w, bool hidden, int num_sms);
 }  // namespace b2m
+
+// ---------------------------------------------------------------------------------------------
+// TensorNet path (kernels_tn.cu).  Per-atom tensors in decomposed form [n][10][64] (I | a_xyz | S_xx xy xz yy yz zz).
+// ---------------------------------------------------------------------------------------------
+namespace b2m {
+struct TnRadial {
+  int nr;       // Gaussian centres in use
+  int nrp;      // row pitch of the rbf / g_rbf buffers (multiple of 64, padding columns zero)
+  float width;  // exp(-width (d - mu_k)^2)
+  float rc;     // cosine cutoff radius
+  float mu[64];
+};
+// C[z][M,N] = epi(A[z][M,K] @ B[K,N] + bias); z-batched over the 10 rows of a decomposed tensor when nz = 10
+// (A + z*zA, C + z*zC, B = bsel ? (z==0 ? B0 : z<4 ? B1 : B2) : B0).  B is [K][N] row-major.  K % 32 == 0, N % 64 == 0.
+// epi 0: store | 1: Cpre = value, C = SiLU(value) | 2: value *= SiLU'(Pre[m][n]) ; accum adds the old C afterwards.
+struct TnGemm {
+  const float* A = nullptr;
+  int lda = 0;
+  int64_t zA = 0;
+  const float *B0 = nullptr, *B1 = nullptr, *B2 = nullptr;
+  int bsel = 0;
+  float* C = nullptr;
+  int ldc = 0;
+  int64_t zC = 0;
+  float* Cpre = nullptr;
+  const float* Pre = nullptr;
+  int ldp = 0;
+  const float* bias = nullptr;
+  int M = 0, N = 0, K = 0, accum = 0, epi = 0;
+};
+void launch_tn_gemm(cudaStream_t st, const TnGemm& g, int nz);
+void launch_tn_edge_geom(cudaStream_t st, int64_t E, const float4* e_vec, const TnRadial& rp, float* rbf, float* cut);
+void launch_tn_embed_agg(cudaStream_t st, int n_own, const int* row_ptr, const int* e_src, const int* type,
+                         const float* U, const float* V, const float* P, const float* cut, const float4* e_vec,
+                         float* T0, float* nr0);
+void launch_tn_layernorm(cudaStream_t st, int rows, int W, const float* x, const float* gamma, const float* beta,
+                         float* y, float* stats);
+void launch_tn_layernorm_bwd(cudaStream_t st, int rows, int W, const float* x, const float* stats, const float* gamma,
+                             const float* gy, float* gx);
+void launch_tn_embed_out(cudaStream_t st, int n, const float* T0m, const float* s2p, float* X0);
+void launch_tn_embed_out_bwd(cudaStream_t st, int n, const float* T0m, const float* s2p, const float* gX0, float* gT0m,
+                             float* gs2p);
+void launch_tn_norm_bwd_add(cudaStream_t st, int n, const float* T0, const float* gnr0, float* gT0);
+void launch_tn_embed_agg_bwd(cudaStream_t st, int64_t E, const int* e_src, const int* e_dst, const int* type,
+                             const float* U, const float* V, const float* P, const float* cut, const float4* e_vec,
+                             const float* gT0, float* gP, float* gC, float* gvh);
+void launch_tn_scale(cudaStream_t st, int n, const float* X, float* Xh, float* q);
+void launch_tn_scale_bwd(cudaStream_t st, int n, const float* X, const float* q, float* g);
+void launch_tn_msg(cudaStream_t st, int n_own, const int* row_ptr, const int* e_src, const float* f3p, const float* cut,
+                   const float* Y, float* msg);
+void launch_tn_msg_bwd(cudaStream_t st, int n_own, const int* row_ptr, const int* e_src, const float* f3p,
+                       const float* cut, const float* Y, const float* gmsg, float* gf, float* gY);
+void launch_tn_edge_act_bwd(cudaStream_t st, int64_t E, const float* f3p, const float* cut, float* gf, float* gC);
+void launch_tn_prod(cudaStream_t st, int n, const float* msg, const float* Y, int so3, float* Pn);
+void launch_tn_prod_bwd(cudaStream_t st, int n, const float* msg, const float* Y, int so3, const float* gPn,
+                        float* gmsg, float* gY);
+void launch_tn_update(cudaStream_t st, int n, const float* Xh, const float* dX, float* Xn);
+void launch_tn_update_bwd(cudaStream_t st, int n, const float* dX, const float* gXn, float* gdX);
+void launch_tn_invariants(cudaStream_t st, int n, const float* X, float* inv);
+void launch_tn_invariants_bwd(cudaStream_t st, int n, const float* X, const float* ginv, float* gX);
+void launch_tn_readout_final(cudaStream_t st, int n, int W, const float* hL, const float* wL, float bL, const float* hG,
+                             const float* wG, float bG, const int* type, const double* eref, float scale, float* lout,
+                             float* gout, float* e_atom, double* energy);
+void launch_tn_readout_seed(cudaStream_t st, int n, int W, const float* lout, const float* gout, float scale,
+                            const float* wL, const float* wG, const float* preL, const float* preG, float* gL,
+                            float* gG);
+void launch_tn_edge_final(cudaStream_t st, int64_t E, const int* e_src, const int* e_dst, const float4* e_vec,
+                          const int* gid, const TnRadial& rp, const float* g_rbf, const float* gC, const float* gvh,
+                          float* gd, float* forces, double* virial);
+}  // namespace b2m

@@ -30,7 +30,7 @@ class Potential_Dist:
         assert getattr(self.model, "dist_enabled", False), "Distributed mode must be enabled"
         assert hasattr(self.model, "gpus"), "Model should have gpus attribute"
         if calc_repuls:
-            raise NotImplementedError("ZBL repulsion is not part of the CHGNet hot path")
+            raise NotImplementedError("ZBL repulsion is not part of the CHGNet / TensorNet paths")
         self.calc_forces = calc_forces
         self.calc_stresses = calc_stresses
         self.calc_hessian = calc_hessian
@@ -65,9 +65,11 @@ class Potential_Dist:
         model._finalize(self.data_mean, self.data_std, self.element_refs)
         dist_info = Distributed.create_distributed(
             cart_coords=cart_coords, frac_coords=None, lattice_matrix=lattice_matrix,
-            num_partitions=model._engine.world, pbc=pbc, use_bond_graph=True, cutoff=float(model.cutoff),
-            three_body_cutoff=float(model.three_body_cutoff), tol=tol, num_threads=1, engine=model._engine,
-            species=species)
+            num_partitions=model._engine.world, pbc=pbc,
+            use_bond_graph=model.use_bond_graph if hasattr(model, "use_bond_graph") else False,  # pes.py:79-80
+            cutoff=float(model.cutoff),
+            three_body_cutoff=float(model.three_body_cutoff) if hasattr(model, "three_body_cutoff") else 0,
+            tol=tol, num_threads=1, engine=model._engine, species=species)
         self.last_dist_info = dist_info
         model_out = model.potential_forward_dist(dist_info, atoms, lattice_matrix, self.calc_stresses,
                                                  self.calc_forces, self.calc_hessian, state_attr)

@@ -78,6 +78,25 @@ int b2m_create(const b2m_model_desc* desc, const int* devices, int ndev, b2m_han
 int b2m_destroy(b2m_handle h);
 const char* b2m_last_error(b2m_handle h);
 
+/* TensorNet: the same handle type and every call below, for a model with matgl's TensorNet attribute
+ * tree (DistMLIP/implementations/matgl/models/tensornet.py:163-204: bond_expansion, tensor_embedding, layers, out_norm,
+ * linear, final_layer).  Supported: units = 64, Gaussian bond expansion (<= 64 centres), swish, O(3) or SO(3),
+ * is_intensive = False, no state features.  No bond graph: use_bond_graph False, three_body_cutoff 0 (pes.py:79-80).
+ * b2m_get_sitewise is an error on such a handle. */
+typedef struct {
+  int32_t n_elem;    /* len(element_types)                                            */
+  int32_t units;     /* 64                                                            */
+  int32_t num_rbf;   /* Gaussian centres (the centres themselves are a state_dict key) */
+  int32_t n_blocks;  /* interaction layers                                            */
+  int32_t so3;       /* equivariance_invariance_group: 0 = "O(3)", 1 = "SO(3)"       */
+  int32_t reserved;
+  double cutoff;     /* r_cut (Angstrom), also the cosine cutoff radius               */
+  double rbf_width;  /* exp(-width (d - mu)^2)                                        */
+  double data_mean;
+  double data_std;
+} b2m_tensornet_desc;
+int b2m_create_tensornet(const b2m_tensornet_desc* desc, const int* devices, int ndev, b2m_handle* out);
+
 /* One call per state_dict key of the matgl CHGNet attribute tree, fp32 row-major. */
 int b2m_load_weights(b2m_handle h, const char* name, const float* host_ptr, const int64_t* shape, int ndim);
 /* Optional per-element energy offsets (Potential.element_refs), length n_elem. */
