@@ -248,7 +248,7 @@ class Engine:
 
     def debug_tensor(self, name):
         c = self.counts()
-        cap = max(c["n_angles"], c["n_edges"], c["n_own"] + c["n_halo"], 1) * 64 + 64
+        cap = max(c["n_angles"], 3 * c["n_edges"], 10 * (c["n_own"] + c["n_halo"]), 1) * 64 + 64
         out = np.empty(cap, dtype=np.float32)
         r, k = C.c_int64(), C.c_int64()
         self._ck(self.lib.b2m_debug_tensor(self.h, name.encode(), out.ctypes.data_as(C.POINTER(C.c_float)), cap,
