@@ -271,9 +271,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from distmlip_b200.implementations.matgl import CHGNet_Dist, Potential_Dist
+    from distmlip_b200.implementations.matgl import CHGNet_Dist, Potential_Dist, TensorNet_Dist
     from distmlip_b200.structures import si_diamond
-    from distmlip_b200.random_init import RandomCHGNet  # seeded random-init weights of the CHGNet architecture
+    from distmlip_b200.random_init import RandomCHGNet, RandomTensorNet  # seeded random-init weights of the architectures
+
+    tn = args.model == "tensornet"  # SURVEY 8(f).2, not the metric's model: a reduced line (no roofline / cpu_baseline)
 
     strong = args.weak_cells <= 0
     if args.rough_atoms > 0:  # degree-imbalanced stress structure: random sequential addition, not the metric
@@ -293,13 +295,15 @@ def run_ours(args):
         n = args.weak_cells
         atoms = si_diamond(n, nz=n * world)
     natoms = len(atoms)
-    model = CHGNet_Dist.from_existing(RandomCHGNet(seed=0))
+    make = (lambda: TensorNet_Dist.from_existing(RandomTensorNet(seed=0))) if tn else \
+           (lambda: CHGNet_Dist.from_existing(RandomCHGNet(seed=0)))
+    model = make()
     model.enable_distributed_mode(list(range(world)) if world > 1 else [local])
     pot = Potential_Dist(model=model, calc_forces=True, calc_stresses=True)
     eng = model._engine
 
     def single_partition_potential():
-        m1 = CHGNet_Dist.from_existing(RandomCHGNet(seed=0))
+        m1 = make()
         m1.enable_distributed_mode([local])  # one GPU, one partition (replica mode inside a multi-rank job)
         return Potential_Dist(model=m1, calc_forces=True, calc_stresses=True)
 
@@ -355,7 +359,21 @@ def run_ours(args):
     parity = parity_block(atoms, out, single_partition_potential, rank, world, local, release=eng.release_workspace)
     barrier()
 
-    if rank == 0:
+    if rank == 0 and tn:
+        c = c_final
+        print(json.dumps({
+            "metric": "TensorNet energy+forces+stress throughput (not the headline metric)", "value": value, "unit": "atoms/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"TensorNet (matgl defaults: units 64, 2 blocks, 32 Gaussian rbf, O(3); random-init seed 0) "
+                                   f"on {natoms}-atom perturbed diamond Si, r_cut=5A", "atoms": natoms,
+                       "edges_per_gpu": c["n_edges"], "parallelism": f"slab{world}"},
+            "phase_ms": {"graph_build": tm["graph_ms"], "forward": tm["fwd_ms"], "backward": tm["bwd_ms"]},
+            "gpu_launches": launches, "clocks": clocks, "parity": parity,
+            "e2e": {"value": e2e_val, "unit": "atoms/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": natoms * (24 + 4) + 72 + 12, "d2h_bytes_per_step": natoms * 12 + 8 + 36}}), flush=True)
+    elif rank == 0:
         c = c_final
         peak, peak_src = load_peaks()
         g_ms = float(np.mean(gather_ms))
@@ -420,6 +438,8 @@ def main():
     ap.add_argument("--rough-atoms", type=int, default=0,
                     help="time the degree-imbalanced random-sequential-addition structure with this many atoms instead")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="chgnet", choices=["chgnet", "tensornet"],
+                    help="tensornet: the SURVEY 8(f).2 path (reduced JSON line; the metric and the default are CHGNet)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -168,6 +168,11 @@ void launch_atomconv_bwd_v3(cudaStream_t st, const AtomConvArgs& a, const AtomCo
 // (K,N) in {(64,128), (64,64), (128,64)}.
 void launch_gemm_tc(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M, int N,
                     int K, const float* bias, const float* R, int ldr, bool accum, int num_sms);
+// same kernel with an epilogue (TensorNet edge MLP): epi 1 keeps the pre-activation in Cpre (pitch ldc) and writes
+// SiLU(value) to C; epi 2 multiplies the (accumulated) value by SiLU'(Pre[row][col]) (pitch ldp); epi 0 = plain
+void launch_gemm_tc_epi(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M, int N,
+                        int K, const float* bias, bool accum, int epi, float* Cpre, const float* Pre, int ldp,
+                        int num_sms);
 struct LineTcW {
   const float* Wgcan;   // [2][8192]: first-layer angle block (N=128, K=64) hi, lo
   const float* W2can;   // [4][4096]: second layers (HIDDEN)
@@ -229,8 +234,7 @@ void launch_tn_scale_bwd(cudaStream_t st, int n, const float* X, const float* q,
 void launch_tn_msg(cudaStream_t st, int n_own, const int* row_ptr, const int* e_src, const float* f3p, const float* cut,
                    const float* Y, float* msg);
 void launch_tn_msg_bwd(cudaStream_t st, int n_own, const int* row_ptr, const int* e_src, const float* f3p,
-                       const float* cut, const float* Y, const float* gmsg, float* gf, float* gY);
-void launch_tn_edge_act_bwd(cudaStream_t st, int64_t E, const float* f3p, const float* cut, float* gf, float* gC);
+                       const float* cut, const float* Y, const float* gmsg, float* g3, float* gC, float* gY);
 void launch_tn_prod(cudaStream_t st, int n, const float* msg, const float* Y, int so3, float* Pn);
 void launch_tn_prod_bwd(cudaStream_t st, int n, const float* msg, const float* Y, int so3, const float* gPn,
                         float* gmsg, float* gY);

@@ -1467,10 +1467,13 @@ __global__ void __launch_bounds__(256, 2)
 // profiles/r02a_bench_97k*.json; B2M_GEMM_PIPE=0 selects the first version): the A chunk of the NEXT (tile, K-half) is loaded into registers while the
 // current one is converted, multiplied and written back, and the accumulate / residual rows of an output slab are
 // requested before the TMEM read-back, so that no global load is waited for right after it is issued.
-template <int K, int N>
+// EPI (TensorNet edge MLP): 1 = keep the pre-activation in Cpre and write SiLU(value); 2 = value *= SiLU'(Pre[row][col])
+// (reverse pass; applied after the accumulate, so the last K-chunk of a split product carries it).
+template <int K, int N, int EPI>
 __global__ void __launch_bounds__(256, 2)
     k_gemm_tc_pipe(const float* __restrict__ A, int lda, const float* __restrict__ Bcan, float* __restrict__ C, int ldc,
-                   int M, const float* __restrict__ bias, const float* __restrict__ R, int ldr, int accum) {
+                   int M, const float* __restrict__ bias, const float* __restrict__ R, int ldr, int accum,
+                   float* __restrict__ Cpre, const float* __restrict__ Pre, int ldp) {
   constexpr uint32_t COL_D = 128;
   constexpr uint32_t LBO = (N / 8) * 128;
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
@@ -1608,6 +1611,13 @@ __global__ void __launch_bounds__(256, 2)
             const float4 c = *cp;
             o.x += c.x, o.y += c.y, o.z += c.z, o.w += c.w;
           }
+          if constexpr (EPI == 1) {
+            *reinterpret_cast<float4*>(Cpre + (size_t)row * ldc + col) = o;
+            o = make_float4(silu_(o.x), silu_(o.y), silu_(o.z), silu_(o.w));
+          } else if constexpr (EPI == 2) {
+            const float4 pv = *reinterpret_cast<const float4*>(Pre + (size_t)row * ldp + col);
+            o.x *= dsilu_(pv.x), o.y *= dsilu_(pv.y), o.z *= dsilu_(pv.z), o.w *= dsilu_(pv.w);
+          }
           *cp = o;
         }
       }
@@ -1617,6 +1627,44 @@ __global__ void __launch_bounds__(256, 2)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256u));
+}
+
+template <int K, int N, int EPI>
+static void launch_gemm_tc_epi_t(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M,
+                                 const float* bias, bool accum, float* Cpre, const float* Pre, int ldp, int num_sms) {
+  constexpr size_t bytes = (size_t)(64 + 2 * N * K + 128 * 68) * 4;
+  static PerDeviceOnce attr;
+  if (auto once_ = attr.first(); once_) {
+    B2M_CK(cudaFuncSetAttribute(k_gemm_tc_pipe<K, N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  }
+  const int ntiles = (M + 127) / 128;
+  const int grid = std::min(ntiles, 2 * num_sms);
+  k_gemm_tc_pipe<K, N, EPI><<<grid, 256, bytes, st>>>(A, lda, Bcan, C, ldc, M, bias, nullptr, 0, accum ? 1 : 0, Cpre, Pre,
+                                                      ldp);
+  B2M_CK(cudaGetLastError());
+  g_launch_count++;
+}
+template <int EPI>
+static void launch_gemm_tc_epi_s(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M,
+                                 int N, int K, const float* bias, bool accum, float* Cpre, const float* Pre, int ldp,
+                                 int num_sms) {
+  if (K == 64 && N == 128)
+    launch_gemm_tc_epi_t<64, 128, EPI>(st, A, lda, Bcan, C, ldc, M, bias, accum, Cpre, Pre, ldp, num_sms);
+  else if (K == 64 && N == 64)
+    launch_gemm_tc_epi_t<64, 64, EPI>(st, A, lda, Bcan, C, ldc, M, bias, accum, Cpre, Pre, ldp, num_sms);
+  else if (K == 128 && N == 64)
+    launch_gemm_tc_epi_t<128, 64, EPI>(st, A, lda, Bcan, C, ldc, M, bias, accum, Cpre, Pre, ldp, num_sms);
+  else
+    throw Error(B2M_ERR_INVALID, "gemm_tc shape");
+}
+void launch_gemm_tc_epi(cudaStream_t st, const float* A, int lda, const float* Bcan, float* C, int ldc, int M, int N,
+                        int K, const float* bias, bool accum, int epi, float* Cpre, const float* Pre, int ldp,
+                        int num_sms) {
+  if (M <= 0) return;
+  B2M_REQUIRE(epi == 1 ? Cpre != nullptr : (epi == 2 ? Pre != nullptr : epi == 0), B2M_ERR_INVALID, "gemm_tc epilogue");
+  if (epi == 1) launch_gemm_tc_epi_s<1>(st, A, lda, Bcan, C, ldc, M, N, K, bias, accum, Cpre, Pre, ldp, num_sms);
+  else if (epi == 2) launch_gemm_tc_epi_s<2>(st, A, lda, Bcan, C, ldc, M, N, K, bias, accum, Cpre, Pre, ldp, num_sms);
+  else launch_gemm_tc_epi_s<0>(st, A, lda, Bcan, C, ldc, M, N, K, bias, accum, Cpre, Pre, ldp, num_sms);
 }
 
 template <int K, int N>
@@ -1633,12 +1681,12 @@ static void launch_gemm_tc_t(cudaStream_t st, const float* A, int lda, const flo
   }();
   static PerDeviceOnce attr_pipe;
   if (auto once_ = attr_pipe.first(); once_) {
-    B2M_CK(cudaFuncSetAttribute(k_gemm_tc_pipe<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    B2M_CK(cudaFuncSetAttribute(k_gemm_tc_pipe<K, N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   }
   const int ntiles = (M + 127) / 128;
   const int grid = std::min(ntiles, 2 * num_sms);
   if (pipe)
-    k_gemm_tc_pipe<K, N><<<grid, 256, bytes, st>>>(A, lda, Bcan, C, ldc, M, bias, R, ldr, accum ? 1 : 0);
+    k_gemm_tc_pipe<K, N, 0><<<grid, 256, bytes, st>>>(A, lda, Bcan, C, ldc, M, bias, R, ldr, accum ? 1 : 0, nullptr, nullptr, 0);
   else
     k_gemm_tc<K, N><<<grid, 256, bytes, st>>>(A, lda, Bcan, C, ldc, M, bias, R, ldr, accum ? 1 : 0);
   B2M_CK(cudaGetLastError());

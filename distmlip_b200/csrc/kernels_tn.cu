@@ -431,47 +431,43 @@ __global__ void k_tn_msg(int n_own, const int* __restrict__ row_ptr, const int* 
   }
   store10(msg + (size_t)t * TW, c, acc);
 }
-// reverse: gf[e][c,p] = sum_{k in p} gmsg[t]_k Y[s]_k ;  gY[s]_k += fe[e][c,part(k)] gmsg[t]_k
+// reverse of k_tn_msg with the activation folded in (fe = silu(f3p) C):
+//   g3[e][c,p] = C silu'(f3p) sum_{k in p} gmsg[t]_k Y[s]_k      (adjoint of the edge MLP's last pre-activation)
+//   gC[e]     += sum_{c,p} silu(f3p) (...)                        (one warp = 32 channels of one destination: shuffle sum)
+//   gY[s]_k   += fe[e][c,part(k)] gmsg[t]_k
 __global__ void k_tn_msg_bwd(int n_own, const int* __restrict__ row_ptr, const int* __restrict__ e_src,
                              const float* __restrict__ f3p, const float* __restrict__ cut,
-                             const float* __restrict__ Y, const float* __restrict__ gmsg, float* __restrict__ gf,
-                             float* __restrict__ gY) {
+                             const float* __restrict__ Y, const float* __restrict__ gmsg, float* __restrict__ g3,
+                             float* __restrict__ gC, float* __restrict__ gY) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= (int64_t)n_own * TC) return;
-  const int t = (int)(i / TC), c = (int)(i % TC);
+  if (i >= (int64_t)n_own * TC) return;  // n_own * 64 is a multiple of 32: whole warps leave together
+  const int t = (int)(i / TC), c = (int)(i % TC), lane = threadIdx.x & 31;
   float gm[10];
   load10(gmsg + (size_t)t * TW, c, gm);
   for (int e = row_ptr[t]; e < row_ptr[t + 1]; e++) {
     const float ce = cut[e];
     const float* fp = f3p + (size_t)e * (3 * TC) + 3 * c;
-    const float f[3] = {silu_f(fp[0]) * ce, silu_f(fp[1]) * ce, silu_f(fp[2]) * ce};
+    const float pre[3] = {fp[0], fp[1], fp[2]};
+    float sl[3], f[3];
+#pragma unroll
+    for (int p = 0; p < 3; p++) sl[p] = silu_f(pre[p]), f[p] = sl[p] * ce;
     const size_t so = (size_t)e_src[e] * TW;
-    float g3[3] = {0.f, 0.f, 0.f};
+    float gq[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 10; k++) {
-      g3[part_of(k)] = fmaf(gm[k], Y[so + k * TC + c], g3[part_of(k)]);
+      gq[part_of(k)] = fmaf(gm[k], Y[so + k * TC + c], gq[part_of(k)]);
       atomicAdd(&gY[so + k * TC + c], f[part_of(k)] * gm[k]);
     }
-    float* go = gf + (size_t)e * (3 * TC) + 3 * c;
-    go[0] = g3[0], go[1] = g3[1], go[2] = g3[2];
+    float* go = g3 + (size_t)e * (3 * TC) + 3 * c;
+    float sc = 0.f;
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      go[p] = gq[p] * ce * dsilu_f(pre[p]);
+      sc = fmaf(gq[p], sl[p], sc);
+    }
+    for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+    if (lane == 0) atomicAdd(&gC[e], sc);
   }
-}
-// in place on gf[E,3C]: g3 = gf * C * silu'(f3p) ; gC[e] += sum gf * silu(f3p)       (one warp per edge)
-__global__ void k_tn_edge_act_bwd(int64_t E, const float* __restrict__ f3p, const float* __restrict__ cut,
-                                  float* __restrict__ gf, float* __restrict__ gC) {
-  const int64_t e = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= E) return;
-  const float ce = cut[e];
-  float s = 0.f;
-  for (int j = lane; j < 3 * TC; j += 32) {
-    const size_t o = (size_t)e * (3 * TC) + j;
-    const float pre = f3p[o], g = gf[o];
-    s = fmaf(g, silu_f(pre), s);
-    gf[o] = g * ce * dsilu_f(pre);
-  }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) gC[e] += s;
 }
 
 // Pn = dec(P) / (norm + 1),  P = msg Y + Y msg  (O(3))  |  2 Y msg  (SO(3))
@@ -746,11 +742,8 @@ void launch_tn_msg(cudaStream_t st, int n_own, const int* row_ptr, const int* e_
   TN_LAUNCH(k_tn_msg, (int64_t)n_own * TC, st, n_own, row_ptr, e_src, f3p, cut, Y, msg);
 }
 void launch_tn_msg_bwd(cudaStream_t st, int n_own, const int* row_ptr, const int* e_src, const float* f3p,
-                       const float* cut, const float* Y, const float* gmsg, float* gf, float* gY) {
-  TN_LAUNCH(k_tn_msg_bwd, (int64_t)n_own * TC, st, n_own, row_ptr, e_src, f3p, cut, Y, gmsg, gf, gY);
-}
-void launch_tn_edge_act_bwd(cudaStream_t st, int64_t E, const float* f3p, const float* cut, float* gf, float* gC) {
-  TN_LAUNCH(k_tn_edge_act_bwd, E * 32, st, E, f3p, cut, gf, gC);
+                       const float* cut, const float* Y, const float* gmsg, float* g3, float* gC, float* gY) {
+  TN_LAUNCH(k_tn_msg_bwd, (int64_t)n_own * TC, st, n_own, row_ptr, e_src, f3p, cut, Y, gmsg, g3, gC, gY);
 }
 void launch_tn_prod(cudaStream_t st, int n, const float* msg, const float* Y, int so3, float* Pn) {
   TN_LAUNCH(k_tn_prod, (int64_t)n * TC, st, n, msg, Y, so3, Pn);

@@ -15,6 +15,10 @@ __device__ __forceinline__ float sigm_(float x) {
   return r;
 }
 __device__ __forceinline__ float silu_(float x) { return x * sigm_(x); }
+__device__ __forceinline__ float dsilu_(float x) {
+  const float sg = sigm_(x);
+  return sg * (1.f + x * (1.f - sg));
+}
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint32_t tf32_hi_bits(float x) {

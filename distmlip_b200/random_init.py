@@ -74,3 +74,64 @@ class RandomCHGNet:
 
     def state_dict(self):
         return dict(self._sd)
+
+
+class _Holder:
+    """attribute bag standing in for a sub-module (TensorNet_Dist reads bond_expansion.rbf.width / rbf_type)"""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class RandomTensorNet:
+    """Duck-typed stand-in for a matgl TensorNet (constructor defaults: units 64, nblocks 2, 32 Gaussian centres of
+    width 0.5 on [0, cutoff + 1], swish, O(3), is_intensive False) carrying seeded random weights."""
+
+    def __init__(self, seed=0, units=64, nblocks=2, num_rbf=32, cutoff=5.0, width=0.5,
+                 equivariance_invariance_group="O(3)", element_types=DEFAULT_ELEMENTS):
+        self.element_types = tuple(element_types)
+        self.cutoff, self.units, self.nblocks, self.num_rbf = cutoff, units, nblocks, num_rbf
+        self.equivariance_invariance_group = equivariance_invariance_group
+        self.is_intensive, self.rbf_type, self.activation_type = False, "Gaussian", "swish"
+        self.bond_expansion = _Holder(rbf_type="Gaussian", rbf=_Holder(width=width))
+        g = torch.Generator().manual_seed(seed)
+
+        def lin(out_f, in_f, bias=True, prefix=""):
+            b = 1.0 / math.sqrt(in_f)
+            d = {prefix + "weight": (torch.rand(out_f, in_f, generator=g) * 2 - 1) * b}
+            if bias:
+                d[prefix + "bias"] = (torch.rand(out_f, generator=g) * 2 - 1) * b
+            return d
+
+        C = units
+        sd = {"bond_expansion.rbf.centers": torch.linspace(0.0, cutoff + 1.0, num_rbf)}
+        te = "tensor_embedding."
+        for k in (1, 2, 3):
+            sd.update(lin(C, num_rbf, True, te + f"distance_proj{k}."))
+        sd[te + "emb.weight"] = torch.randn(len(self.element_types), C, generator=g)
+        sd.update(lin(C, 2 * C, True, te + "emb2."))
+        for k in range(3):
+            sd.update(lin(C, C, False, te + f"linears_tensor.{k}."))
+        sd.update(lin(2 * C, C, True, te + "linears_scalar.0."))
+        sd.update(lin(3 * C, 2 * C, True, te + "linears_scalar.1."))
+        sd[te + "init_norm.weight"], sd[te + "init_norm.bias"] = torch.ones(C), torch.zeros(C)
+        for l in range(nblocks):
+            p = f"layers.{l}."
+            sd.update(lin(C, num_rbf, True, p + "linears_scalar.0."))
+            sd.update(lin(2 * C, C, True, p + "linears_scalar.1."))
+            sd.update(lin(3 * C, 2 * C, True, p + "linears_scalar.2."))
+            for k in range(6):
+                sd.update(lin(C, C, False, p + f"linears_tensor.{k}."))
+        sd["out_norm.weight"], sd["out_norm.bias"] = torch.ones(3 * C), torch.zeros(3 * C)
+        sd.update(lin(C, 3 * C, True, "linear."))
+        dims = [C, C, C, C, 1]  # WeightedReadOut(in_feats=units, dims=[units, units], num_targets=1).gated
+        for br in ("layers", "gates"):
+            for j, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+                sd.update(lin(b, a, True, f"final_layer.gated.{br}.{2 * j}."))
+        self._sd = sd
+
+    def to(self, *_args, **_kwargs):
+        return self
+
+    def state_dict(self):
+        return dict(self._sd)

@@ -55,3 +55,13 @@ def test_oracle_symmetries():
     E2, F2, _ = potential_ref(m, b, dtype=torch.float64)
     assert abs(float(E2 - E)) < 1e-9
     assert np.abs(F2.numpy() - F.numpy() @ R.T).max() < 1e-9
+
+
+def test_random_init_model_has_the_oracle_state_dict():
+    """bench.py's product-side random TensorNet carries exactly the tensors of the restated module tree"""
+    from distmlip_b200.random_init import RandomTensorNet
+
+    a, b = RandomTensorNet(seed=0).state_dict(), TensorNetRef().state_dict()
+    assert set(a) == set(b)
+    assert all(tuple(a[k].shape) == tuple(b[k].shape) for k in a)
+    assert torch.allclose(a["bond_expansion.rbf.centers"], b["bond_expansion.rbf.centers"])
