@@ -243,7 +243,7 @@ static void tn_alloc_workspace(b2m_engine* e) {
   }
   {
     t.gX.ensure(nl * TNW + 64), t.gY.ensure(nl * TNW + 64), t.gmsg.ensure(no * TNW + 64), t.gdX.ensure(no * TNW + 64);
-    t.gPn.ensure(no * TNW + 64), t.gf.ensure(E * 3 * C + 64), t.g2.ensure(E * 2 * C + 64), t.g1.ensure(E * C + 64);
+    t.gPn.ensure(no * TNW + 64), t.gf.ensure(E * 3 * C + 64);  // the reverse edge MLP reuses f2 / f1 (forward scratch) for its adjoints
     t.g_rbf.ensure(E * nrp + 64), t.gC.ensure(E + 64), t.gvh.ensure(E * 3 + 64), t.gd.ensure(E + 64);
     t.gT0m.ensure(no * TNW + 64), t.gT0.ensure(no * TNW + 64), t.gs2p.ensure(no * 3 * C + 64);
     t.gs1p.ensure(no * 2 * C + 64), t.gln0.ensure(no * C + 64), t.gnr0.ensure(no * C + 64);
@@ -309,19 +309,19 @@ static void tn_edge_mlp_bwd(b2m_engine* e, int l) {
   const int E = (int)e->g.E, C = TNC;
   if (t.tc) {  // the 192 -> 128 product as three K-chunks accumulated in place; the last one carries the SiLU' factor
     for (int j = 0; j < 3; j++)
-      launch_gemm_tc_epi(e->st, t.gf.p + j * C, 3 * C, w.W2rc[j], t.g2.p, 2 * C, E, 2 * C, C, nullptr, j > 0, j == 2 ? 2 : 0,
+      launch_gemm_tc_epi(e->st, t.gf.p + j * C, 3 * C, w.W2rc[j], t.f2.p, 2 * C, E, 2 * C, C, nullptr, j > 0, j == 2 ? 2 : 0,
                          nullptr, j == 2 ? t.f2p[l].p : nullptr, 2 * C, e->num_sms);
-    launch_gemm_tc_epi(e->st, t.g2.p, 2 * C, w.W1rc, t.g1.p, C, E, C, 2 * C, nullptr, false, 2, nullptr, t.f1p[l].p, C, e->num_sms);
+    launch_gemm_tc_epi(e->st, t.f2.p, 2 * C, w.W1rc, t.f1.p, C, E, C, 2 * C, nullptr, false, 2, nullptr, t.f1p[l].p, C, e->num_sms);
     tn_stage(e, "tn_edge_mlp_bwd:launch_gemm_tc_epi@310");
-    launch_gemm_tc_epi(e->st, t.g1.p, C, w.W0rc, t.g_rbf.p, t.rp.nrp, E, t.rp.nrp, C, nullptr, true, 0, nullptr, nullptr, 0,
+    launch_gemm_tc_epi(e->st, t.f1.p, C, w.W0rc, t.g_rbf.p, t.rp.nrp, E, t.rp.nrp, C, nullptr, true, 0, nullptr, nullptr, 0,
                        e->num_sms);
     return;
   }
-  tn_gemm(e, t.gf.p, 3 * C, w.W2r, t.g2.p, 2 * C, E, 2 * C, 3 * C, nullptr, 2, nullptr, t.f2p[l].p, 2 * C);
+  tn_gemm(e, t.gf.p, 3 * C, w.W2r, t.f2.p, 2 * C, E, 2 * C, 3 * C, nullptr, 2, nullptr, t.f2p[l].p, 2 * C);
   tn_stage(e, "tn_edge_mlp_bwd:tn_gemm@315");
-  tn_gemm(e, t.g2.p, 2 * C, w.W1r, t.g1.p, C, E, C, 2 * C, nullptr, 2, nullptr, t.f1p[l].p, C);
+  tn_gemm(e, t.f2.p, 2 * C, w.W1r, t.f1.p, C, E, C, 2 * C, nullptr, 2, nullptr, t.f1p[l].p, C);
   tn_stage(e, "tn_edge_mlp_bwd:tn_gemm@316");
-  tn_gemm(e, t.g1.p, C, w.W0r, t.g_rbf.p, t.rp.nrp, E, t.rp.nrp, C, nullptr, 0, nullptr, nullptr, 0, true);
+  tn_gemm(e, t.f1.p, C, w.W0r, t.g_rbf.p, t.rp.nrp, E, t.rp.nrp, C, nullptr, 0, nullptr, nullptr, 0, true);
   tn_stage(e, "tn_edge_mlp_bwd:tn_gemm@317");
 }
 
@@ -537,8 +537,8 @@ static void tn_release(b2m_engine* e) {
     b.p = nullptr, b.cap = 0;
   };
   for (auto* b : {&t.rbf, &t.cut, &t.P, &t.T0, &t.nr0, &t.ln0, &t.st0, &t.s1p, &t.s1, &t.s2p, &t.T0m, &t.f1, &t.f2, &t.inv,
-                  &t.str, &t.r, &t.xr, &t.lout, &t.gout, &t.e_atom, &t.gX, &t.gY, &t.gmsg, &t.gdX, &t.gPn, &t.gf, &t.g2,
-                  &t.g1, &t.g_rbf, &t.gC, &t.gvh, &t.gd, &t.gT0m, &t.gT0, &t.gs2p, &t.gs1p, &t.gln0, &t.gnr0, &t.gr,
+                  &t.str, &t.r, &t.xr, &t.lout, &t.gout, &t.e_atom, &t.gX, &t.gY, &t.gmsg, &t.gdX, &t.gPn, &t.gf,
+                  &t.g_rbf, &t.gC, &t.gvh, &t.gd, &t.gT0m, &t.gT0, &t.gs2p, &t.gs1p, &t.gln0, &t.gnr0, &t.gr,
                   &t.ginv, &t.gxr, &t.gca, &t.gcb})
     drop(*b);
   for (auto* v : {&t.X, &t.f1p, &t.f2p, &t.f3p, &t.q, &t.Xh, &t.Y, &t.msg, &t.Pn, &t.dX, &t.cpre[0], &t.cpre[1],

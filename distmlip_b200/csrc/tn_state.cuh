@@ -37,13 +37,14 @@ struct TnState {
   float blast[2] = {0.f, 0.f};
   int wlast_in = 64;
   // ---- workspace ----
-  DBuf<float> rbf, cut, P, T0, nr0, ln0, st0, s1p, s1, s2p, T0m, f1, f2;
+  DBuf<float> rbf, cut, P, T0, nr0, ln0, st0, s1p, s1, s2p, T0m;
+  DBuf<float> f1, f2;  // [E][C], [E][2C]: activations of the edge MLP (forward), adjoints of its hidden layers (reverse)
   std::vector<DBuf<float>> X;                                       // nblocks + 1 : [n_loc][10][C]
   std::vector<DBuf<float>> f1p, f2p, f3p, q, Xh, Y, msg, Pn, dX;    // per layer
   DBuf<float> inv, str, r, xr, lout, gout, e_atom;
   std::vector<DBuf<float>> cpre[2], cact[2];
   // reverse pass
-  DBuf<float> gX, gY, gmsg, gdX, gPn, gf, g2, g1, g_rbf, gC, gvh, gd, gT0m, gT0, gs2p, gs1p, gln0, gnr0, gr, ginv, gxr,
+  DBuf<float> gX, gY, gmsg, gdX, gPn, gf, g_rbf, gC, gvh, gd, gT0m, gT0, gs2p, gs1p, gln0, gnr0, gr, ginv, gxr,
       gca, gcb;
 };
 
