@@ -289,18 +289,18 @@ static void tn_edge_mlp(b2m_engine* e, int l) {
   if (t.tc) {  // tcgen05 3xTF32 row GEMM (kernels_tc.cu) with the SiLU epilogue; the 128 -> 192 layer as three column blocks
     launch_gemm_tc_epi(e->st, t.rbf.p, t.rp.nrp, w.W0c, t.f1.p, C, E, C, C, w.b0, false, 1, t.f1p[l].p, nullptr, 0, e->num_sms);
     launch_gemm_tc_epi(e->st, t.f1.p, C, w.W1c, t.f2.p, 2 * C, E, 2 * C, C, w.b1, false, 1, t.f2p[l].p, nullptr, 0, e->num_sms);
-    tn_stage(e, "tn_edge_mlp:launch_gemm_tc_epi@291");
+    tn_stage(e, "tn_edge_mlp:launch_gemm_tc_epi");
     for (int j = 0; j < 3; j++)
       launch_gemm_tc_epi(e->st, t.f2.p, 2 * C, w.W2c[j], t.f3p[l].p + j * C, 3 * C, E, C, 2 * C, w.b2 + j * C, false, 0,
                          nullptr, nullptr, 0, e->num_sms);
     return;
   }
   tn_gemm(e, t.rbf.p, t.rp.nrp, w.W0t, t.f1.p, C, E, C, t.rp.nrp, w.b0, 1, t.f1p[l].p);
-  tn_stage(e, "tn_edge_mlp:tn_gemm@297");
+  tn_stage(e, "tn_edge_mlp:tn_gemm");
   tn_gemm(e, t.f1.p, C, w.W1t, t.f2.p, 2 * C, E, 2 * C, C, w.b1, 1, t.f2p[l].p);
-  tn_stage(e, "tn_edge_mlp:tn_gemm@298");
+  tn_stage(e, "tn_edge_mlp:tn_gemm");
   tn_gemm(e, t.f2.p, 2 * C, w.W2t, t.f3p[l].p, 3 * C, E, 3 * C, 2 * C, w.b2);
-  tn_stage(e, "tn_edge_mlp:tn_gemm@299");
+  tn_stage(e, "tn_edge_mlp:tn_gemm");
 }
 // reverse of the edge MLP: g3 [E,3C] (adjoint of the last pre-activation) -> g_rbf += ...
 static void tn_edge_mlp_bwd(b2m_engine* e, int l) {
@@ -312,17 +312,17 @@ static void tn_edge_mlp_bwd(b2m_engine* e, int l) {
       launch_gemm_tc_epi(e->st, t.gf.p + j * C, 3 * C, w.W2rc[j], t.f2.p, 2 * C, E, 2 * C, C, nullptr, j > 0, j == 2 ? 2 : 0,
                          nullptr, j == 2 ? t.f2p[l].p : nullptr, 2 * C, e->num_sms);
     launch_gemm_tc_epi(e->st, t.f2.p, 2 * C, w.W1rc, t.f1.p, C, E, C, 2 * C, nullptr, false, 2, nullptr, t.f1p[l].p, C, e->num_sms);
-    tn_stage(e, "tn_edge_mlp_bwd:launch_gemm_tc_epi@310");
+    tn_stage(e, "tn_edge_mlp_bwd:launch_gemm_tc_epi");
     launch_gemm_tc_epi(e->st, t.f1.p, C, w.W0rc, t.g_rbf.p, t.rp.nrp, E, t.rp.nrp, C, nullptr, true, 0, nullptr, nullptr, 0,
                        e->num_sms);
     return;
   }
   tn_gemm(e, t.gf.p, 3 * C, w.W2r, t.f2.p, 2 * C, E, 2 * C, 3 * C, nullptr, 2, nullptr, t.f2p[l].p, 2 * C);
-  tn_stage(e, "tn_edge_mlp_bwd:tn_gemm@315");
+  tn_stage(e, "tn_edge_mlp_bwd:tn_gemm");
   tn_gemm(e, t.f2.p, 2 * C, w.W1r, t.f1.p, C, E, C, 2 * C, nullptr, 2, nullptr, t.f1p[l].p, C);
-  tn_stage(e, "tn_edge_mlp_bwd:tn_gemm@316");
+  tn_stage(e, "tn_edge_mlp_bwd:tn_gemm");
   tn_gemm(e, t.f1.p, C, w.W0r, t.g_rbf.p, t.rp.nrp, E, t.rp.nrp, C, nullptr, 0, nullptr, nullptr, 0, true);
-  tn_stage(e, "tn_edge_mlp_bwd:tn_gemm@317");
+  tn_stage(e, "tn_edge_mlp_bwd:tn_gemm");
 }
 
 static void tn_forward(b2m_engine* e) {
@@ -333,7 +333,7 @@ static void tn_forward(b2m_engine* e) {
   const int E = (int)g.E;
   B2M_CK(cudaMemsetAsync(e->scal.p, 0, 16 * sizeof(double), e->st));
   launch_tn_edge_geom(e->st, g.E, g.e_vec.p, t.rp, t.rbf.p, t.cut.p);
-  tn_stage(e, "tn_forward:launch_tn_edge_geom@327");
+  tn_stage(e, "tn_forward:launch_tn_edge_geom");
   // ---- embedding (tensor_embedding_dist, tensornet.py:104-112) ----
   if (t.tc) {
     launch_gemm_tc_epi(e->st, t.rbf.p, t.rp.nrp, t.Wdc_a, t.P.p, 3 * C, E, 2 * C, C, t.bd, false, 0, nullptr, nullptr, 0, e->num_sms);
@@ -341,55 +341,55 @@ static void tn_forward(b2m_engine* e) {
                        e->num_sms);
   } else {
     tn_gemm(e, t.rbf.p, t.rp.nrp, t.Wd_t, t.P.p, 3 * C, E, 3 * C, t.rp.nrp, t.bd);
-    tn_stage(e, "tn_forward:tn_gemm@334");
+    tn_stage(e, "tn_forward:tn_gemm");
   }
   launch_tn_embed_agg(e->st, no, g.row_ptr.p, g.e_src.p, g.type.p, t.U, t.V, t.P.p, t.cut.p, g.e_vec.p, t.T0.p, t.nr0.p);
-  tn_stage(e, "tn_forward:launch_tn_embed_agg@336");
+  tn_stage(e, "tn_forward:launch_tn_embed_agg");
   launch_tn_layernorm(e->st, no, C, t.nr0.p, t.ln0_g, t.ln0_b, t.ln0.p, t.st0.p);
-  tn_stage(e, "tn_forward:launch_tn_layernorm@337");
+  tn_stage(e, "tn_forward:launch_tn_layernorm");
   tn_gemm(e, t.ln0.p, C, t.Ws0_t, t.s1.p, 2 * C, no, 2 * C, C, t.bs0, 1, t.s1p.p);
-  tn_stage(e, "tn_forward:tn_gemm@338");
+  tn_stage(e, "tn_forward:tn_gemm");
   tn_gemm(e, t.s1.p, 2 * C, t.Ws1_t, t.s2p.p, 3 * C, no, 3 * C, 2 * C, t.bs1);
-  tn_stage(e, "tn_forward:tn_gemm@339");
+  tn_stage(e, "tn_forward:tn_gemm");
   tn_mix(e, t.T0.p, t.T0m.p, no, t.Wte_t[0], t.Wte_t[1], t.Wte_t[2]);
-  tn_stage(e, "tn_forward:tn_mix@340");
+  tn_stage(e, "tn_forward:tn_mix");
   launch_tn_embed_out(e->st, no, t.T0m.p, t.s2p.p, t.X[0].p);
-  tn_stage(e, "tn_forward:launch_tn_embed_out@341");
+  tn_stage(e, "tn_forward:launch_tn_embed_out");
   // ---- interaction layers (dist_forward, tensornet.py:119-127) ----
   for (int l = 0; l < nb; l++) {
     const TnLayerW& w = t.L[l];
     halo_forward_begin(e, 2, l);  // halo rows of X[l] travel while the edge MLP of this layer runs
     tn_edge_mlp(e, l);
-    tn_stage(e, "tn_forward:tn_edge_mlp@346");
+    tn_stage(e, "tn_forward:tn_edge_mlp");
     halo_forward_end(e);
-    tn_stage(e, "tn_forward:halo_forward_end@347");
+    tn_stage(e, "tn_forward:halo_forward_end");
     launch_tn_scale(e->st, nl, t.X[l].p, t.Xh[l].p, t.q[l].p);
-    tn_stage(e, "tn_forward:launch_tn_scale@348");
+    tn_stage(e, "tn_forward:launch_tn_scale");
     tn_mix(e, t.Xh[l].p, t.Y[l].p, nl, w.Wt_t[0], w.Wt_t[1], w.Wt_t[2]);
-    tn_stage(e, "tn_forward:tn_mix@349");
+    tn_stage(e, "tn_forward:tn_mix");
     launch_tn_msg(e->st, no, g.row_ptr.p, g.e_src.p, t.f3p[l].p, t.cut.p, t.Y[l].p, t.msg[l].p);
-    tn_stage(e, "tn_forward:launch_tn_msg@350");
+    tn_stage(e, "tn_forward:launch_tn_msg");
     launch_tn_prod(e->st, no, t.msg[l].p, t.Y[l].p, t.so3, t.Pn[l].p);
-    tn_stage(e, "tn_forward:launch_tn_prod@351");
+    tn_stage(e, "tn_forward:launch_tn_prod");
     tn_mix(e, t.Pn[l].p, t.dX[l].p, no, w.Wt_t[3], w.Wt_t[4], w.Wt_t[5]);
-    tn_stage(e, "tn_forward:tn_mix@352");
+    tn_stage(e, "tn_forward:tn_mix");
     launch_tn_update(e->st, no, t.Xh[l].p, t.dX[l].p, t.X[l + 1].p);
-    tn_stage(e, "tn_forward:launch_tn_update@353");
+    tn_stage(e, "tn_forward:launch_tn_update");
   }
   // ---- readout (tensornet.py:129-147; the transfer after the last layer feeds nothing and is skipped) ----
   launch_tn_invariants(e->st, no, t.X[nb].p, t.inv.p);
-  tn_stage(e, "tn_forward:launch_tn_invariants@356");
+  tn_stage(e, "tn_forward:launch_tn_invariants");
   launch_tn_layernorm(e->st, no, 3 * C, t.inv.p, t.lnr_g, t.lnr_b, t.r.p, t.str.p);
-  tn_stage(e, "tn_forward:launch_tn_layernorm@357");
+  tn_stage(e, "tn_forward:launch_tn_layernorm");
   tn_gemm(e, t.r.p, 3 * C, t.Wl_t, t.xr.p, C, no, C, 3 * C, t.bl);
-  tn_stage(e, "tn_forward:tn_gemm@358");
+  tn_stage(e, "tn_forward:tn_gemm");
   const float* hlast[2];
   for (int br = 0; br < 2; br++) {
     const float* h = t.xr.p;
     for (size_t j = 0; j < t.chain[br].size(); j++) {
       const TnChainW& cw = t.chain[br][j];
       tn_gemm(e, h, cw.in, cw.Wt, t.cact[br][j].p, cw.out, no, cw.out, cw.in, cw.b, 1, t.cpre[br][j].p);
-      tn_stage(e, "tn_forward:tn_gemm@364");
+      tn_stage(e, "tn_forward:tn_gemm");
       h = t.cact[br][j].p;
     }
     hlast[br] = h;
@@ -403,13 +403,13 @@ static void tn_backward(b2m_engine* e) {
   Graph& g = e->g;
   const int C = TNC, nb = t.nblocks, no = g.n_own, nl = g.n_loc, E = (int)g.E;
   launch_zero_rows(e->st, t.gC.p, g.E);
-  tn_stage(e, "tn_backward:launch_zero_rows@377");
+  tn_stage(e, "tn_backward:launch_zero_rows");
   launch_zero_rows(e->st, t.g_rbf.p, g.E * t.rp.nrp);
-  tn_stage(e, "tn_backward:launch_zero_rows@378");
+  tn_stage(e, "tn_backward:launch_zero_rows");
   launch_zero_rows(e->st, t.gX.p, (int64_t)nl * TNW);
-  tn_stage(e, "tn_backward:launch_zero_rows@379");
+  tn_stage(e, "tn_backward:launch_zero_rows");
   launch_zero_rows(e->st, e->forces.p, g.N * 3);
-  tn_stage(e, "tn_backward:launch_zero_rows@380");
+  tn_stage(e, "tn_backward:launch_zero_rows");
   // ---- readout ----
   const int nh = (int)t.chain[0].size();
   launch_tn_readout_seed(e->st, no, t.wlast_in, t.lout.p, t.gout.p, (float)e->desc.data_std, t.wlast[0], t.wlast[1],
@@ -421,53 +421,53 @@ static void tn_backward(b2m_engine* e) {
       // (g_pre_j @ W_j) * SiLU'(pre_{j-1}); the widths of a chain are equal in matgl's readout, so in place is not
       // possible (the GEMM reads its input rows while writing): ping-pong through gr (free until the chains are done)
       tn_gemm(e, cur, cw.out, cw.Wr, t.gr.p, cw.in, no, cw.in, cw.out, nullptr, 2, nullptr, t.cpre[br][j - 1].p, cw.in);
-      tn_stage(e, "tn_backward:tn_gemm@391");
+      tn_stage(e, "tn_backward:tn_gemm");
       B2M_CK(cudaMemcpyAsync(cur, t.gr.p, (size_t)no * cw.in * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
     }
     const TnChainW& c0 = t.chain[br][0];
     tn_gemm(e, cur, c0.out, c0.Wr, t.gxr.p, c0.in, no, c0.in, c0.out, nullptr, 0, nullptr, nullptr, 0, br == 1);
-    tn_stage(e, "tn_backward:tn_gemm@395");
+    tn_stage(e, "tn_backward:tn_gemm");
   }
   tn_gemm(e, t.gxr.p, C, t.Wl_r, t.gr.p, 3 * C, no, 3 * C, C, nullptr);
-  tn_stage(e, "tn_backward:tn_gemm@397");
+  tn_stage(e, "tn_backward:tn_gemm");
   launch_tn_layernorm_bwd(e->st, no, 3 * C, t.inv.p, t.str.p, t.lnr_g, t.gr.p, t.ginv.p);
-  tn_stage(e, "tn_backward:launch_tn_layernorm_bwd@398");
+  tn_stage(e, "tn_backward:launch_tn_layernorm_bwd");
   launch_tn_invariants_bwd(e->st, no, t.X[nb].p, t.ginv.p, t.gX.p);
-  tn_stage(e, "tn_backward:launch_tn_invariants_bwd@399");
+  tn_stage(e, "tn_backward:launch_tn_invariants_bwd");
   // ---- interaction layers ----
   for (int l = nb - 1; l >= 0; l--) {
     const TnLayerW& w = t.L[l];
     launch_tn_update_bwd(e->st, no, t.dX[l].p, t.gX.p, t.gdX.p);  // gX stays: it is also the adjoint of Xh (residual)
     tn_mix(e, t.gdX.p, t.gPn.p, no, w.Wt_r[3], w.Wt_r[4], w.Wt_r[5]);
-    tn_stage(e, "tn_backward:tn_mix@404");
+    tn_stage(e, "tn_backward:tn_mix");
     launch_zero_rows(e->st, t.gY.p + (size_t)no * TNW, (int64_t)(nl - no) * TNW);
-    tn_stage(e, "tn_backward:launch_zero_rows@405");
+    tn_stage(e, "tn_backward:launch_zero_rows");
     launch_tn_prod_bwd(e->st, no, t.msg[l].p, t.Y[l].p, t.so3, t.gPn.p, t.gmsg.p, t.gY.p);
-    tn_stage(e, "tn_backward:launch_tn_prod_bwd@406");
+    tn_stage(e, "tn_backward:launch_tn_prod_bwd");
     launch_tn_msg_bwd(e->st, no, g.row_ptr.p, g.e_src.p, t.f3p[l].p, t.cut.p, t.Y[l].p, t.gmsg.p, t.gf.p, t.gC.p, t.gY.p);
-    tn_stage(e, "tn_backward:launch_tn_msg_bwd@407");
+    tn_stage(e, "tn_backward:launch_tn_msg_bwd");
     tn_edge_mlp_bwd(e, l);
-    tn_stage(e, "tn_backward:tn_edge_mlp_bwd@408");
+    tn_stage(e, "tn_backward:tn_edge_mlp_bwd");
     tn_mix(e, t.gY.p, t.gX.p, nl, w.Wt_r[0], w.Wt_r[1], w.Wt_r[2], true);
-    tn_stage(e, "tn_backward:tn_mix@409");
+    tn_stage(e, "tn_backward:tn_mix");
     launch_tn_scale_bwd(e->st, nl, t.X[l].p, t.q[l].p, t.gX.p);
-    tn_stage(e, "tn_backward:launch_tn_scale_bwd@410");
+    tn_stage(e, "tn_backward:launch_tn_scale_bwd");
     halo_backward(e, t.gX.p, false, TNW);
-    tn_stage(e, "tn_backward:halo_backward@411");
+    tn_stage(e, "tn_backward:halo_backward");
   }
   // ---- embedding ----
   launch_tn_embed_out_bwd(e->st, no, t.T0m.p, t.s2p.p, t.gX.p, t.gT0m.p, t.gs2p.p);
-  tn_stage(e, "tn_backward:launch_tn_embed_out_bwd@414");
+  tn_stage(e, "tn_backward:launch_tn_embed_out_bwd");
   tn_gemm(e, t.gs2p.p, 3 * C, t.Ws1_r, t.gs1p.p, 2 * C, no, 2 * C, 3 * C, nullptr, 2, nullptr, t.s1p.p, 2 * C);
-  tn_stage(e, "tn_backward:tn_gemm@415");
+  tn_stage(e, "tn_backward:tn_gemm");
   tn_gemm(e, t.gs1p.p, 2 * C, t.Ws0_r, t.gln0.p, C, no, C, 2 * C, nullptr);
-  tn_stage(e, "tn_backward:tn_gemm@416");
+  tn_stage(e, "tn_backward:tn_gemm");
   launch_tn_layernorm_bwd(e->st, no, C, t.nr0.p, t.st0.p, t.ln0_g, t.gln0.p, t.gnr0.p);
-  tn_stage(e, "tn_backward:launch_tn_layernorm_bwd@417");
+  tn_stage(e, "tn_backward:launch_tn_layernorm_bwd");
   tn_mix(e, t.gT0m.p, t.gT0.p, no, t.Wte_r[0], t.Wte_r[1], t.Wte_r[2]);
-  tn_stage(e, "tn_backward:tn_mix@418");
+  tn_stage(e, "tn_backward:tn_mix");
   launch_tn_norm_bwd_add(e->st, no, t.T0.p, t.gnr0.p, t.gT0.p);
-  tn_stage(e, "tn_backward:launch_tn_norm_bwd_add@419");
+  tn_stage(e, "tn_backward:launch_tn_norm_bwd_add");
   launch_tn_embed_agg_bwd(e->st, g.E, g.e_src.p, g.e_dst.p, g.type.p, t.U, t.V, t.P.p, t.cut.p, g.e_vec.p, t.gT0.p,
                           t.gf.p, t.gC.p, t.gvh.p);
   if (t.tc) {
@@ -476,7 +476,7 @@ static void tn_backward(b2m_engine* e) {
                          nullptr, 0, e->num_sms);
   } else {
     tn_gemm(e, t.gf.p, 3 * C, t.Wd_r, t.g_rbf.p, t.rp.nrp, E, t.rp.nrp, 3 * C, nullptr, 0, nullptr, nullptr, 0, true);
-    tn_stage(e, "tn_backward:tn_gemm@427");
+    tn_stage(e, "tn_backward:tn_gemm");
   }
   launch_tn_edge_final(e->st, g.E, g.e_src.p, g.e_dst.p, g.e_vec.p, g.gid.p, t.rp, t.g_rbf.p, t.gC.p, t.gvh.p, t.gd.p,
                        e->forces.p, e->scal.p + 1);

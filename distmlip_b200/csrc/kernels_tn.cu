@@ -695,6 +695,8 @@ __global__ void __launch_bounds__(256) k_tn_edge_final(int64_t E, const int* __r
 void launch_tn_gemm(cudaStream_t st, const TnGemm& g, int nz) {
   if (g.M <= 0) return;
   B2M_REQUIRE(g.K % 32 == 0 && g.N % 64 == 0 && g.lda % 4 == 0 && g.ldc % 4 == 0, B2M_ERR_INVALID, "tn gemm shape");
+  B2M_REQUIRE(g.epi == 0 || (nz == 1 && (g.epi == 1 ? g.Cpre != nullptr : g.Pre != nullptr)), B2M_ERR_INVALID,
+              "tn gemm epilogue");  // the epilogue pointers carry no z offset
   dim3 grid(cdiv(g.M, 128), g.N / 64, nz);
   k_tn_gemm<<<grid, 256, 0, st>>>(g);
   B2M_CK(cudaGetLastError());

@@ -38,7 +38,12 @@ class TensorNet_Dist(EngineBackedModel):
         rbf_type = self._attr("rbf_type", None) or getattr(self._attr("bond_expansion"), "rbf_type", "Gaussian")
         if str(rbf_type) != "Gaussian" or "bond_expansion.rbf.centers" not in sd:
             raise NotImplementedError(f"rbf_type={rbf_type!r}: the engine implements the Gaussian bond expansion only")
-        group_name = str(self._attr("equivariance_invariance_group", "O(3)"))
+        group_name = self._attr("equivariance_invariance_group")
+        if group_name is None:  # matgl keeps the group on the interaction layers
+            layers_mod = self._attr("layers")
+            first = layers_mod[0] if layers_mod is not None and len(layers_mod) else None
+            group_name = getattr(first, "equivariance_invariance_group", "O(3)")
+        group_name = str(group_name)
         if group_name not in ("O(3)", "SO(3)"):
             raise NotImplementedError(f"equivariance_invariance_group={group_name!r}")
         if any(k.startswith("tensor_embedding.") and "state" in k for k in sd):
