@@ -9,8 +9,11 @@
 // (linears_tensor) act on each of the 10 rows with the weight of its part, so they are one z-batched row GEMM; the
 // element-wise tensor algebra is one thread per (atom, channel), coalesced over channels; aggregations walk the
 // CSR-by-destination rows (no atomics in the forward); the reverse pass scatters to sources with red.add.
-// First generation of this path: FP32 FFMA tiles throughout (the tcgen05 GEMM of the CHGNet path covers K,N in
-// {64,128} only; moving the edge MLP onto it is the next step).
+// First generation of this path.  The edge-level products (edge MLP 32 -> 64 -> 128 -> 192 and the three distance
+// projections, 49 % of a step) run on the tcgen05 row GEMM of the CHGNet path (kernels_tc.cu, k_gemm_tc_pipe with a
+// SiLU / SiLU' epilogue; engine_tn.inl composes the 192-wide layers from its 64/128 shapes); the node-level products
+// (channel mixes, scalar MLPs, readout) use the FP32-FFMA tile kernel below, which also serves the edge level under
+// B2M_TN_FFMA=1 (A/B checks).  DESIGN.md 8 lists what comes next.
 #include <math_constants.h>
 
 #include "kernels.cuh"
